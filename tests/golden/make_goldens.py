@@ -1,0 +1,301 @@
+"""Generate golden vectors by running the *reference* SceneRF renderer (unmodified, imported from
+/root/reference) on the deterministic synthetic inputs of scenerf_b200.synth.
+
+Runs ONLY in the build container (needs /root/reference); the GPU box never executes this.
+    python tests/golden/make_goldens.py            # rewrites tests/golden/*.npz
+
+How the reference is made importable without touching it:
+  * `pytorch_lightning` is absent -> a 10-line stand-in module whose LightningModule is nn.Module;
+  * `UNet2DSphere.build` would call torch.hub (network) -> replaced by a stub returning nn.Identity.
+The two RNG draws of a chunk (utils.py:84 torch.rand_like, utils.py:208-211 torch.normal) are recorded by
+wrapping the torch functions, so that every other implementation can be fed identical noise.
+
+Stored per case: inputs that are not regenerable from synth (noise), stage-boundary tensors and the 12-key
+output dict of render_rays_batch (scenerf.py:456-469).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("SCENERF_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from scenerf_b200 import synth  # noqa: E402
+
+
+def _install_shims():
+    pl = types.ModuleType("pytorch_lightning")
+
+    class _LM(nn.Module):
+        def save_hyperparameters(self, *a, **k):
+            pass
+
+        def log(self, *a, **k):
+            pass
+
+        @property
+        def device(self):
+            return next(self.parameters()).device
+
+    pl.LightningModule = _LM
+    sys.modules["pytorch_lightning"] = pl
+    import scenerf.models.unet2d_sphere as U
+    U.UNet2DSphere.build = classmethod(lambda cls, **kw: nn.Identity())
+
+
+def build_reference_model(cfg: synth.SceneConfig, seed=11):
+    _install_shims()
+    if cfg.dataset == "kitti":
+        from scenerf.models.scenerf import SceneRF
+    else:
+        from scenerf.models.scenerf_bf import SceneRF
+    m = SceneRF(som_sigma=cfg.som_sigma, std=cfg.std, img_size=(cfg.img_W, cfg.img_H),
+                max_sample_depth=cfg.max_sample_depth, n_gaussians=cfg.n_gaussians,
+                n_pts_uni=cfg.n_pts_uni, n_pts_per_gaussian=cfg.n_pts_per_gaussian,
+                add_fov_hor=cfg.add_fov_hor, add_fov_ver=cfg.add_fov_ver,
+                sphere_H=cfg.sphere_H, sphere_W=cfg.sphere_W).eval()
+    pm, pg = synth.make_model_params(cfg, seed)
+    m.mlp.load_state_dict({k: torch.from_numpy(v) for k, v in pm.items()})
+    m.mlp_gaussian.load_state_dict({k: torch.from_numpy(v) for k, v in pg.items()})
+    return m
+
+
+class _Recorder:
+    """Records the reference's RNG draws and a few stage-boundary tensors."""
+
+    def __init__(self, model):
+        self.model = model
+        self.rec = {}
+        self._orig = {}
+
+    def __enter__(self):
+        import scenerf.models.utils as RU
+        rec = self.rec
+        o_rand_like, o_normal = torch.rand_like, torch.normal
+        self._orig = dict(rand_like=o_rand_like, normal=o_normal)
+
+        def rand_like(x, *a, **k):
+            r = o_rand_like(x, *a, **k)
+            rec.setdefault("noise_u", []).append(r.detach().clone())
+            return r
+
+        def normal(*a, **k):
+            r = o_normal(*a, **k)
+            rec.setdefault("noise_n", []).append(r.detach().clone())
+            return r
+
+        torch.rand_like, torch.normal = rand_like, normal
+        sm = self.model.spherical_mapping
+        o_from = sm.from_pixels
+        self._orig["from_pixels"] = o_from
+
+        def from_pixels(inv_K, pix_coords=None):
+            out = o_from(inv_K=inv_K, pix_coords=pix_coords)
+            rec.setdefault("sphere_coords", []).append(out[1].detach().clone())
+            rec.setdefault("proj_pix", []).append(pix_coords.detach().clone())
+            return out
+
+        sm.from_pixels = from_pixels
+        o_predict = self.model.predict
+        self._orig["predict"] = o_predict
+
+        def predict(*a, **k):
+            rec.setdefault("predict_cam_pts", []).append(k["cam_pts"].detach().clone())
+            rec.setdefault("predict_viewdir", []).append(k["viewdir"].detach().clone())
+            out = o_predict(*a, **k)
+            if isinstance(out, tuple):
+                rec.setdefault("predict_density", []).append(out[0].detach().clone())
+                rec.setdefault("predict_color", []).append(out[1].detach().clone())
+            else:
+                rec.setdefault("predict_offset", []).append(out.detach().clone())
+            return out
+
+        self.model.predict = predict
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand_like, torch.normal = self._orig["rand_like"], self._orig["normal"]
+        self.model.spherical_mapping.from_pixels = self._orig["from_pixels"]
+        self.model.predict = self._orig["predict"]
+
+
+def run_render_case(cfg, pixels, pyr_seed, torch_seed=0, **model_kw):
+    model = build_reference_model(cfg, **model_kw)
+    x_rgb = {k: torch.from_numpy(v) for k, v in synth.make_pyramid(pyr_seed, cfg.sphere_W, cfg.sphere_H).items()}
+    K = torch.from_numpy(cfg.K)
+    T = torch.from_numpy(cfg.T)
+    pix = torch.from_numpy(pixels)
+    torch.manual_seed(torch_seed)
+    with torch.no_grad(), _Recorder(model) as r:
+        if cfg.dataset == "kitti":
+            out = model.render_rays_batch(K, T, x_rgb, ray_batch_size=pix.shape[0], sampled_pixels=pix)
+        else:
+            out = model.render_rays_batch(K, T, x_rgb, sampled_pixels=pix, ray_batch_size=pix.shape[0])
+    rec = r.rec
+    R = pix.shape[0]
+    g = {k: v.numpy() for k, v in out.items()}
+    g["noise_u"] = rec["noise_u"][0].reshape(R, -1).numpy()
+    g["noise_n"] = rec["noise_n"][0].reshape(R, -1).numpy()
+    # predict call 0 = gaussian proposal (R,G,3) ; call 1 = main pass (R,S,3)
+    g["gauss_pts"] = rec["predict_cam_pts"][0].numpy()
+    g["gauss_offset"] = rec["predict_offset"][0].numpy()
+    g["main_pts"] = rec["predict_cam_pts"][1].numpy()
+    g["viewdir"] = rec["predict_viewdir"][1].numpy()
+    g["main_color"] = rec["predict_color"][0].numpy()
+    g["gauss_sphere"] = rec["sphere_coords"][0].numpy().astype(np.int32)
+    g["main_sphere"] = rec["sphere_coords"][1].numpy().astype(np.int32)
+    g["pixels"] = pixels
+    return g
+
+
+def run_predict_case(cfg, cam_pts, viewdir, pyr_seed, **model_kw):
+    """Direct call of SceneRF.predict (scenerf.py:505-547) on crafted points (adversarial gather cases)."""
+    model = build_reference_model(cfg, **model_kw)
+    x_rgb = {k: torch.from_numpy(v) for k, v in synth.make_pyramid(pyr_seed, cfg.sphere_W, cfg.sphere_H).items()}
+    K = torch.from_numpy(cfg.K)
+    with torch.no_grad(), _Recorder(model) as r:
+        kw = dict(mlp=model.mlp, cam_pts=torch.from_numpy(cam_pts), x_rgb=x_rgb, cam_K=K,
+                  viewdir=torch.from_numpy(viewdir))
+        if cfg.dataset == "kitti":
+            kw["T_cam2velo"] = None
+        density, color = model.predict(**kw)
+        kw["mlp"] = model.mlp_gaussian
+        offset = model.predict(output_type="offset", **kw)
+    return dict(cam_pts=cam_pts, viewdir=viewdir, density=density.numpy(), color=color.numpy(),
+                offset=offset.numpy(), sphere=r.rec["sphere_coords"][0].numpy().astype(np.int32),
+                proj_pix=r.rec["proj_pix"][0].numpy())
+
+
+def adversarial_points(cfg, n_cols=48, n_per=8, seed=5):
+    """Points (in the infer-camera frame) whose sphere coordinates land where the reference's quirks bite
+    (SURVEY 8a a7/a10): top-left (W//s,H//s) corners of scales 2..16 incl. the boundary row/column, points
+    behind the camera (pixel sentinel (-1,-1)), points outside the sphere grid, and ordinary points."""
+    v_min, v_max, h_min, h_max = cfg.angles()
+    W, H = cfg.sphere_W, cfg.sphere_H
+    targets = []
+    for s in (1, 2, 4, 8, 16):
+        wn, hn = W // s, H // s
+        for sx in (0, 1, wn // 2, wn - 1, wn, wn + 1):
+            for sy in (0, 1, hn // 2, hn - 1, hn, hn + 1):
+                targets.append((sx, sy))
+    targets = targets[: n_cols * n_per - 64] if len(targets) > n_cols * n_per - 64 else targets
+    pts = []
+    u = synth.hash_unit(seed, 4 * len(targets)).astype(np.float64)
+    for i, (sx, sy) in enumerate(targets):
+        # invert the angle mapping (spherical_mapping.py:95-115) at the pixel centre (+ small jitter)
+        h = h_min + (sx + 0.3 * (u[4 * i] - 0.5)) / (W - 1) * (h_max - h_min)
+        v = v_min + (sy + 0.3 * (u[4 * i + 1] - 0.5)) / (H - 1) * (v_max - v_min)
+        hr, vr = np.deg2rad(180.0 - h), np.deg2rad(v)
+        d = np.array([np.sin(vr) * np.cos(hr), -np.cos(vr), np.sin(vr) * np.sin(hr)])
+        r = 2.0 + 30.0 * u[4 * i + 2]
+        pts.append(d * r)
+    pts = np.array(pts, dtype=np.float32)
+    n_total = n_cols * n_per
+    extra = n_total - pts.shape[0]
+    e = synth.hash_uniform(seed + 1, 3 * extra).reshape(extra, 3)
+    ex = np.stack([e[:, 0] * 30.0, e[:, 1] * 6.0, e[:, 2] * 40.0 + 10.0], axis=1).astype(np.float32)
+    ex[: extra // 4, 2] = -np.abs(ex[: extra // 4, 2])          # behind the camera
+    ex[extra // 4: extra // 2, 0] *= 8.0                         # far outside the horizontal FOV
+    pts = np.concatenate([pts, ex], axis=0)
+    cam_pts = pts.reshape(n_cols, n_per, 3)
+    viewdir = (synth.hash_uniform(seed + 2, n_cols * 3).reshape(n_cols, 3) * np.float32(0.8)).astype(np.float32)
+    return np.ascontiguousarray(cam_pts), np.ascontiguousarray(viewdir)
+
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+@case
+def kitti_mini():
+    cfg = synth.config_A(name="kitti_mini", sphere_W=300, sphere_H=90, yaw_deg=10.0, tz=1.0)
+    return run_render_case(cfg, synth.random_pixels(21, 96, cfg.img_W, cfg.img_H), pyr_seed=31)
+
+
+@case
+def kitti_s128():
+    cfg = synth.config_B(name="kitti_s128", sphere_W=306, sphere_H=92)
+    pix = synth.grid_pixels(cfg.img_W, cfg.img_H, stride=61)[:48]
+    return run_render_case(cfg, np.ascontiguousarray(pix), pyr_seed=32)
+
+
+@case
+def bf_mini():
+    cfg = synth.config_C(name="bf_mini", sphere_W=160, sphere_H=120, n_pts_uni=32)
+    return run_render_case(cfg, synth.random_pixels(23, 64, cfg.img_W, cfg.img_H), pyr_seed=33)
+
+
+@case
+def kitti_identity():
+    """T = identity-ish (tz=0): all samples of a ray share one sphere pixel (SURVEY hard part 3c)."""
+    cfg = synth.config_A(name="kitti_identity", sphere_W=300, sphere_H=90, yaw_deg=0.0, tz=0.0)
+    return run_render_case(cfg, synth.random_pixels(24, 32, cfg.img_W, cfg.img_H), pyr_seed=34)
+
+
+@case
+def predict_adversarial_kitti():
+    cfg = synth.config_A(name="adv_kitti", sphere_W=300, sphere_H=90)
+    pts, vd = adversarial_points(cfg)
+    return run_predict_case(cfg, pts, vd, pyr_seed=35)
+
+
+@case
+def predict_adversarial_kitti_full():
+    """Reference-default sphere grid 1500x452: W_t != W_n for scales 8/16 (fractional taps)."""
+    cfg = synth.config_A(name="adv_kitti_full")
+    pts, vd = adversarial_points(cfg, n_cols=40, n_per=8)
+    return run_predict_case(cfg, pts, vd, pyr_seed=36)
+
+
+@case
+def predict_adversarial_bf():
+    cfg = synth.config_C(name="adv_bf", sphere_W=160, sphere_H=120)
+    pts, vd = adversarial_points(cfg)
+    pts = pts * np.float32(0.2)
+    return run_predict_case(cfg, pts, vd, pyr_seed=37)
+
+
+@case
+def angles_kat():
+    """The only known-answer check in the reference: scripts/determine_angles.py <-> scenerf.py:84-87 and
+    scenerf_bf.py:84-87.  We run the same functions on every pixel and store min/max."""
+    _install_shims()
+    from scenerf.models.spherical_mapping import SphericalMapping, pix_2_cam_pts
+    out = {}
+    for name, K, W, H in (("kitti", synth.KITTI_K, 1220, 370), ("bf", synth.BF_K, 640, 480)):
+        invK = torch.inverse(torch.from_numpy(K))
+        m = SphericalMapping(v_angle_max=0, v_angle_min=0, h_angle_max=0, h_angle_min=0, img_W=W, img_H=H,
+                             out_img_W=0, out_img_H=0)
+        mesh = np.meshgrid(range(W), range(H), indexing="xy")
+        ids = torch.from_numpy(np.stack(mesh, 0).astype(np.float32))
+        pix = torch.cat([ids[0].reshape(-1, 1), ids[1].reshape(-1, 1)], 1)
+        cam = pix_2_cam_pts(pix, invK, torch.ones(pix.shape[0]))
+        v, h, _ = m.cam_pts_2_angle(cam)
+        out[name] = np.array([v.min(), v.max(), h.min(), h.max()], dtype=np.float32)
+    return out
+
+
+def main():
+    only = sys.argv[1:]
+    for name, fn in CASES.items():
+        if only and name not in only:
+            continue
+        g = fn()
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **g)
+        print("%-32s %8.1f KB  keys=%d" % (name, os.path.getsize(path) / 1024.0, len(g)))
+
+
+if __name__ == "__main__":
+    main()
