@@ -76,10 +76,22 @@ def test_render_rays_batch_vs_reference(name):
            scale=np.abs(g["depth_volumes"]).max())
     amin_ok = clean & (o.debug["argmin_margin"] > 1e-3)
     _close(out["weights_at_depth"][amin_ok], g["weights_at_depth"][amin_ok], "weights_at_depth")
-    som_ok = clean & (o.debug["som_margin"] > 1e-4)
-    assert som_ok.mean() > 0.5
-    _close(out["loss_kl"][som_ok], g["loss_kl"][som_ok], "loss_kl", rtol=1e-4)
-    _close(out["som_vars"][som_ok], g["som_vars"][som_ok], "som_vars", rtol=1e-4)
+    _check_som(out, g, clean, o.debug["som_margin"])
+
+
+def _check_som(out, g, clean, margin, rtol=1e-4):
+    """loss_kl / som_vars (ray_som_kl.py:10-78) hinge on a per-sample arg-max over prototypes.  For samples far from
+    every gaussian all candidates are equal up to the last ulp of exp(), so the reference's own choice there is
+    round-off; a ray may disagree only if it contains such a (near-)tie, and only a small fraction may."""
+    bad = np.zeros(clean.shape, bool)
+    for k in ("loss_kl", "som_vars"):
+        a, b = out[k], g[k]
+        tol = ATOL + rtol * max(1.0, float(np.abs(b).max()))
+        err = np.abs(a - b).reshape(a.shape[0], -1).max(axis=1)
+        bad |= err > tol
+    bad &= clean
+    assert not (bad & (margin > 1e-5)).any(), "SOM outputs differ on rays without an arg-max near-tie"
+    assert bad.mean() <= 0.1, "SOM outputs differ on %d of %d rays" % (bad.sum(), bad.size)
 
 
 @pytest.mark.parametrize("name", sorted(PREDICT_CASES))
