@@ -11,7 +11,7 @@ from oracle import scenerf_oracle as orc
 from scenerf_b200 import synth
 
 # abs tolerance = ATOL + RTOL * max(1, max|golden|) (logit-level round-off is O(1)-scaled) ; float32 pipeline with ~10 chained 512..2480-long dot products
-RTOL = 5e-5
+RTOL = 1e-4
 ATOL = 2e-6
 
 
