@@ -1,0 +1,168 @@
+/*
+ * scenerf_b200 -- C ABI of the Blackwell (sm_100a) ray renderer that replaces the hot path of
+ * astra-vision/SceneRF: `SceneRF.render_rays_batch` (reference scenerf/models/scenerf.py:392-471, BundleFusion twin
+ * scenerf/models/scenerf_bf.py:420-494) and everything below it.
+ *
+ * The reference has no FFI: its boundary is a bound Python method.  This header is the boundary a maintainer binds
+ * instead (ctypes stub in INTEGRATION.md; scenerf_b200/renderer.py is that binding).  Conventions:
+ *   - plain C, no torch types; every `*_dev` pointer is a CUDA device pointer, every `*_host` pointer host memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); no call synchronises the device
+ *     except the *_host entry points;
+ *   - no hidden device allocations: packed buffers and workspace are supplied by the caller (sizes from the
+ *     *_bytes functions); the library never falls back to a CPU path;
+ *   - return value 0 = ok, otherwise an SRF_E_* code and a message in srf_last_error() (thread-local).
+ * The reference raises Python exceptions for bad shapes (torch) -- the Python binding turns non-zero codes into
+ * RuntimeError / ValueError.
+ */
+#ifndef SCENERF_B200_H
+#define SCENERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRF_ABI_VERSION 1
+#define SRF_NUM_SCALES 5   /* x_rgb keys "1_1","1_2","1_4","1_8","1_16" (unet2d_sphere.py:200-206) */
+#define SRF_NUM_BLOCKS 3   /* ResnetFC n_blocks (scenerf.py:100-114) */
+#define SRF_D_HIDDEN 512
+#define SRF_D_X 42         /* 39 positional-encoding + 3 view direction (scenerf.py:101) */
+#define SRF_MAX_GAUSSIANS 8
+
+enum srf_status {
+  SRF_OK = 0,
+  SRF_E_INVALID = 1,   /* bad argument / shape */
+  SRF_E_WORKSPACE = 2, /* workspace or packed buffer too small */
+  SRF_E_CUDA = 3,      /* CUDA runtime error (message has the cudaError string) */
+  SRF_E_UNSUPPORTED = 4
+};
+
+enum srf_precision {
+  SRF_PREC_FP32 = 0, /* SIMT fp32 FMA everywhere: strict mode, matches the reference to float32 round-off */
+  SRF_PREC_FP16_TC = 1 /* tcgen05 tensor cores: fp16 operands, fp32 accumulate in TMEM */
+};
+
+enum srf_dataset { SRF_KITTI = 0, SRF_BUNDLEFUSION = 1 };
+
+/* The 22 tensors of one ResnetFC exactly as nn.Linear stores them: weight (out,in) row-major fp32, bias (out).
+ * Reference: scenerf/models/resnetfc.py:66-131; state-dict names in comments. */
+typedef struct srf_mlp_weights {
+  int d_out;                               /* 4 for `mlp`, 2 for `mlp_gaussian` */
+  int d_latent;                            /* 2480 = sum of pyramid channels */
+  const float* lin_in_w;                   /* lin_in.weight   (512, 42)   */
+  const float* lin_in_b;                   /* lin_in.bias     (512)       */
+  const float* lin_z_w[SRF_NUM_BLOCKS];    /* lin_z.b.weight  (512, 2480) */
+  const float* lin_z_b[SRF_NUM_BLOCKS];    /* lin_z.b.bias    (512)       */
+  const float* fc0_w[SRF_NUM_BLOCKS];      /* blocks.b.fc_0.weight (512,512) */
+  const float* fc0_b[SRF_NUM_BLOCKS];
+  const float* fc1_w[SRF_NUM_BLOCKS];      /* blocks.b.fc_1.weight (512,512) */
+  const float* fc1_b[SRF_NUM_BLOCKS];
+  const float* lin_out_w;                  /* lin_out.weight  (d_out, 512) */
+  const float* lin_out_b;
+  const void* tc_packed;                   /* srf_pack_weights_tc() output, or NULL if only fp32 mode is used */
+} srf_mlp_weights;
+
+/* Feature pyramid of ONE input image, repacked channels-last ([H][W][C] fp32) by srf_pack_pyramid().
+ * Reference input: x_rgb dict of CHW tensors, consumed at scenerf.py:522-525 / utils.py:232-247. */
+typedef struct srf_pyramid {
+  const float* hwc[SRF_NUM_SCALES];
+  int C[SRF_NUM_SCALES], H[SRF_NUM_SCALES], W[SRF_NUM_SCALES];
+} srf_pyramid;
+
+/* Hyper-parameters the path reads from the module (scenerf.py:23-115) + per-call camera and pose. */
+typedef struct srf_config {
+  int dataset;               /* srf_dataset: selects the +1.5 / +0.5 constant (scenerf.py:592 vs scenerf_bf.py:606) */
+  int n_pts_uni;             /* U */
+  int n_gaussians;           /* G */
+  int n_pts_per_gaussian;    /* P ; samples per ray S = U + G*P */
+  float max_sample_depth;
+  float base_std;            /* self.std */
+  float som_sigma;
+  int sphere_W, sphere_H;    /* out_img_W / out_img_H */
+  int d_latent;              /* total pyramid channels (ResnetFC d_latent); 0 means the reference's 2480 */
+  float v_angle_min, v_angle_max, h_angle_min, h_angle_max; /* SphericalMapping angles incl. add_fov */
+  float K[9];                /* cam_K row-major */
+  float inv_K[9];            /* torch.inverse(cam_K) (scenerf.py:401) -- supplied by the caller so that it is bit-equal */
+  float T[16];               /* T_source2infer row-major */
+  int precision;             /* srf_precision */
+  uint64_t seed;             /* in-kernel Philox seed when noise pointers are NULL */
+  int flags;                 /* SRF_FLAG_* */
+} srf_config;
+
+#define SRF_FLAG_SKIP_ZERO_CHUNKS 1 /* tensor-core path: skip K-chunks of lin_z whose gathered features are all
+                                       zero for the whole 128-point tile (bit-identical result) */
+
+/* Outputs of render_rays_batch: the 12-key dict of scenerf.py:456-469.  Any pointer may be NULL (not written);
+ * inference callers need only depth and color.  All fp32, ray order = input order, samples sorted by distance. */
+typedef struct srf_outputs {
+  float* depth;                 /* (R)   */
+  float* color;                 /* (R,3) */
+  float* gaussian_means;        /* (R,G) */
+  float* gaussian_stds;         /* (R,G) */
+  float* weights_at_depth;      /* (R)   */
+  float* closest_pts_to_depths; /* (R)   */
+  float* loss_kl;               /* (R)   */
+  float* alphas;                /* (R,S) */
+  float* som_vars;              /* (R,G) */
+  float* densities;             /* (R,S) */
+  float* weights;               /* (R,S) */
+  float* depth_volumes;         /* (R,S) */
+  float* som_means;             /* (R,G) extra: RaySOM new_means (ray_som_kl.py:78), not part of the dict */
+  int32_t* dbg_sphere_main;     /* (R*S,2) extra: rounded sphere coords of the main pass (parity diagnostics) */
+  int32_t* dbg_sphere_gauss;    /* (R*G,2) */
+} srf_outputs;
+
+int srf_abi_version(void);
+const char* srf_last_error(void);
+/* sizeof() of the ABI structs as the library was compiled: 0 srf_config, 1 srf_pyramid, 2 srf_mlp_weights,
+ * 3 srf_outputs -- lets a foreign-language binding verify its struct layout at load time. */
+size_t srf_sizeof(int which);
+
+/* --- one-time packing ------------------------------------------------------------------------------------- */
+size_t srf_pyramid_bytes(const int* C, const int* H, const int* W);
+/* CHW fp32 (device) -> HWC fp32 into dst_dev; fills *out.  Replaces nothing in the reference: it is the layout
+ * change that makes the 4-tap gather of utils.py:239-245 read contiguous channels. */
+int srf_pack_pyramid(const float* const* chw_dev, const int* C, const int* H, const int* W, void* dst_dev,
+                     size_t dst_bytes, srf_pyramid* out, void* stream);
+
+size_t srf_tc_weights_bytes(int d_out, int d_latent);
+/* fp32 nn.Linear tensors -> fp16 K-major, 128B-swizzled shared-memory stage images in MMA consumption order. */
+int srf_pack_weights_tc(const srf_mlp_weights* w, void* dst_dev, size_t dst_bytes, void* stream);
+
+/* --- the hot path ----------------------------------------------------------------------------------------- */
+size_t srf_render_workspace_bytes(const srf_config* cfg, int n_rays);
+
+/* SceneRF.render_rays_batch (scenerf.py:392-471) for one chunk-free batch of rays.
+ *   pixels_dev (R,2) fp32 (x,y);  noise_u_dev (R,U) U[0,1) or NULL;  noise_n_dev (R,G*P) N(0,1) or NULL
+ *   (the two RNG draws of utils.py:84 and utils.py:208-211; NULL = Philox from cfg->seed). */
+int srf_render_rays(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w_main,
+                    const srf_mlp_weights* w_gauss, const float* pixels_dev, int n_rays, const float* noise_u_dev,
+                    const float* noise_n_dev, const srf_outputs* out, void* workspace_dev, size_t workspace_bytes,
+                    void* stream);
+
+/* Same call with HOST buffers for pixels and outputs (pinned or pageable): H2D of the rays, render, D2H of the
+ * requested outputs, stream synchronised on return.  out_host pointers are host pointers. */
+int srf_render_rays_host(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w_main,
+                         const srf_mlp_weights* w_gauss, const float* pixels_host, int n_rays,
+                         const srf_outputs* out_host, void* workspace_dev, size_t workspace_bytes, void* stream);
+size_t srf_render_host_workspace_bytes(const srf_config* cfg, int n_rays);
+
+/* SceneRF.predict (scenerf.py:505-547): points already in the infer-camera frame.
+ *   cam_pts_dev (n_cols*n_per,3); viewdir_dev (n_cols,3) shared by the n_per points of a column;
+ *   raw_out_dev (n, d_out) = ResnetFC output before activation, or NULL;
+ *   density_dev (n) = softplus(out[3]-1), color_dev (n,3) = sigmoid(out[:3]) (d_out==4 only), or NULL. */
+size_t srf_predict_workspace_bytes(const srf_config* cfg, int n_points);
+int srf_predict(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w, const float* cam_pts_dev,
+                const float* viewdir_dev, int n_cols, int n_per, float* raw_out_dev, float* density_dev,
+                float* color_dev, int32_t* dbg_sphere_dev, void* workspace_dev, size_t workspace_bytes,
+                void* stream);
+
+/* Number of kernels the last srf_render_rays / srf_predict call on this thread launched (bench "gpu_launches"). */
+int srf_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCENERF_B200_H */

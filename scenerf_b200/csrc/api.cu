@@ -1,0 +1,379 @@
+// extern "C" boundary of libscenerf_b200.so (declarations + contract: include/scenerf_b200.h).
+// Sequences the kernels of one render_rays_batch call on the caller's stream:
+//   ray_setup -> point MLP (mlp_gaussian, R*G points) -> sample_sort -> point MLP (mlp, R*S points) -> composite_som
+// which is scenerf/models/scenerf.py:598-700 (batchify_depth_and_color) without the Python chunk loop of :419-442.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include "kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SRF_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return SRF_OK;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// bump allocator over the caller-supplied workspace
+struct Arena {
+  unsigned char* base;
+  size_t cap, off;
+  template <typename T>
+  T* take(size_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += align256(count * sizeof(T));
+    return p;
+  }
+};
+
+int validate(const srf_config* cfg, const srf_pyramid* pyr) {
+  if (!cfg) return fail(SRF_E_INVALID, "cfg is NULL");
+  if (cfg->n_gaussians < 1 || cfg->n_gaussians > SRF_MAX_GAUSSIANS)
+    return fail(SRF_E_INVALID, "n_gaussians=%d outside [1,%d]", cfg->n_gaussians, SRF_MAX_GAUSSIANS);
+  if (cfg->n_pts_uni < 1 || cfg->n_pts_per_gaussian < 1)
+    return fail(SRF_E_INVALID, "n_pts_uni=%d n_pts_per_gaussian=%d must be >= 1", cfg->n_pts_uni,
+                cfg->n_pts_per_gaussian);
+  const int S = cfg->n_pts_uni + cfg->n_gaussians * cfg->n_pts_per_gaussian;
+  if (S > 256) return fail(SRF_E_INVALID, "samples per ray S=%d exceeds 256", S);
+  if (cfg->sphere_W < 2 || cfg->sphere_H < 2) return fail(SRF_E_INVALID, "sphere grid %dx%d", cfg->sphere_W, cfg->sphere_H);
+  if (cfg->precision != SRF_PREC_FP32 && cfg->precision != SRF_PREC_FP16_TC)
+    return fail(SRF_E_INVALID, "unknown precision %d", cfg->precision);
+  if (pyr) {
+    for (int s = 0; s < SRF_NUM_SCALES; ++s) {
+      if (!pyr->hwc[s] || pyr->C[s] < 1 || pyr->H[s] < 1 || pyr->W[s] < 1)
+        return fail(SRF_E_INVALID, "pyramid scale %d is empty", s);
+      if (pyr->C[s] % 8) return fail(SRF_E_INVALID, "pyramid scale %d: C=%d must be a multiple of 8", s, pyr->C[s]);
+    }
+  }
+  return SRF_OK;
+}
+
+int validate_weights(const srf_mlp_weights* w, int d_out, int d_latent, int precision) {
+  if (!w) return fail(SRF_E_INVALID, "weights are NULL");
+  if (w->d_out != d_out) return fail(SRF_E_INVALID, "ResnetFC d_out=%d, expected %d", w->d_out, d_out);
+  if (w->d_latent != d_latent)
+    return fail(SRF_E_INVALID, "ResnetFC d_latent=%d but the pyramid has %d channels", w->d_latent, d_latent);
+  if (precision == SRF_PREC_FP16_TC && !w->tc_packed)
+    return fail(SRF_E_INVALID, "precision=FP16_TC needs srf_pack_weights_tc() output in tc_packed");
+  if (precision == SRF_PREC_FP32) {
+    bool ok = w->lin_in_w && w->lin_in_b && w->lin_out_w && w->lin_out_b;
+    for (int b = 0; b < SRF_NUM_BLOCKS; ++b)
+      ok = ok && w->lin_z_w[b] && w->lin_z_b[b] && w->fc0_w[b] && w->fc0_b[b] && w->fc1_w[b] && w->fc1_b[b];
+    if (!ok) return fail(SRF_E_INVALID, "a ResnetFC tensor pointer is NULL");
+  }
+  return SRF_OK;
+}
+
+srf::DevParams make_params(const srf_config* cfg, const srf_pyramid* pyr) {
+  srf::DevParams p;
+  memset(&p, 0, sizeof(p));
+  memcpy(p.K, cfg->K, sizeof(p.K));
+  memcpy(p.invK, cfg->inv_K, sizeof(p.invK));
+  memcpy(p.T, cfg->T, sizeof(p.T));
+  // python: h_fov = abs(h_max - h_min) in double, cast to fp32 when it meets the tensor (spherical_mapping.py:68-69,108-109)
+  p.v_min = cfg->v_angle_min;
+  p.h_min = cfg->h_angle_min;
+  p.v_fov = (float)fabs((double)cfg->v_angle_max - (double)cfg->v_angle_min);
+  p.h_fov = (float)fabs((double)cfg->h_angle_max - (double)cfg->h_angle_min);
+  p.sphere_W = cfg->sphere_W;
+  p.sphere_H = cfg->sphere_H;
+  p.sphW1 = (float)(cfg->sphere_W - 1);
+  p.sphH1 = (float)(cfg->sphere_H - 1);
+  p.max_depth = cfg->max_sample_depth;
+  p.base_std = cfg->base_std;
+  p.add_const = cfg->dataset == SRF_KITTI ? 1.5f : 0.5f;
+  p.som_sigma = cfg->som_sigma;
+  const double step = (double)cfg->max_sample_depth * 1.0 / cfg->n_gaussians;          // scenerf.py:554
+  p.g_start = (float)(step / 2);
+  p.g_end = (float)((double)cfg->max_sample_depth - step / 2);
+  p.uni_step = (float)(((double)cfg->max_sample_depth - 0.2) / cfg->n_pts_uni);        // utils.py:77
+  p.two_sig2 = (float)(2.0 * (double)cfg->som_sigma * (double)cfg->som_sigma);
+  p.U = cfg->n_pts_uni;
+  p.G = cfg->n_gaussians;
+  p.P = cfg->n_pts_per_gaussian;
+  p.S = p.U + p.G * p.P;
+  p.seed = cfg->seed;
+  if (pyr) {
+    int off = 0;
+    for (int s = 0; s < SRF_NUM_SCALES; ++s) {
+      const int scale = 1 << s;
+      p.feat[s] = pyr->hwc[s];
+      p.C[s] = pyr->C[s]; p.H[s] = pyr->H[s]; p.W[s] = pyr->W[s];
+      p.ch_off[s] = off;
+      off += pyr->C[s];
+      // scenerf.py:522-525: scale 1 normalised by (out_img_W, out_img_H), scale s by (W//s, H//s)
+      p.normW[s] = (float)(cfg->sphere_W / scale);
+      p.normH[s] = (float)(cfg->sphere_H / scale);
+      p.halfW[s] = (float)(pyr->W[s] / 2.0);
+      p.halfH[s] = (float)(pyr->H[s] / 2.0);
+    }
+    p.ch_off[SRF_NUM_SCALES] = off;
+    p.d_latent = off;
+  }
+  return p;
+}
+
+size_t mlp_workspace_bytes(int precision, int d_latent, int n_points) {
+  return precision == SRF_PREC_FP32 ? srf::simt_workspace_bytes(d_latent, n_points)
+                                    : srf::tc_workspace_bytes(d_latent, n_points);
+}
+
+int run_mlp(const srf::DevParams& p, int precision, int flags, const srf_mlp_weights& w, const float* pts,
+            const float* viewdir, int n, int n_per, float* raw, int32_t* dbg, void* ws, size_t ws_bytes,
+            cudaStream_t st) {
+  int l;
+  if (precision == SRF_PREC_FP32) l = srf::run_point_mlp_simt(p, w, pts, viewdir, n, n_per, raw, dbg, ws, ws_bytes, st);
+  else l = srf::run_point_mlp_tc(p, w, pts, viewdir, n, n_per, raw, dbg, flags, ws, ws_bytes, st);
+  if (l < 0) return fail(SRF_E_WORKSPACE, "point-MLP workspace too small (%zu bytes)", ws_bytes);
+  g_launches += l;
+  return check_cuda("point MLP");
+}
+
+int pyramid_channels(const srf_pyramid* pyr) {
+  int c = 0;
+  for (int s = 0; s < SRF_NUM_SCALES; ++s) c += pyr->C[s];
+  return c;
+}
+
+struct RayWorkspace {
+  float *unit, *viewdir, *gauss_pts, *gauss_raw, *means, *stds, *t_sorted, *depth_volume, *pts, *raw;
+  void* mlp_ws;
+  size_t mlp_ws_bytes;
+};
+
+size_t carve(const srf_config* cfg, int R, int d_latent, unsigned char* base, RayWorkspace* out) {
+  const size_t G = cfg->n_gaussians, S = cfg->n_pts_uni + G * cfg->n_pts_per_gaussian;
+  Arena a{base, 0, 0};
+  RayWorkspace w;
+  w.unit = a.take<float>((size_t)R * 3);
+  w.viewdir = a.take<float>((size_t)R * 3);
+  w.gauss_pts = a.take<float>((size_t)R * G * 3);
+  w.gauss_raw = a.take<float>((size_t)R * G * 2);
+  w.means = a.take<float>((size_t)R * G);
+  w.stds = a.take<float>((size_t)R * G);
+  w.t_sorted = a.take<float>((size_t)R * S);
+  w.depth_volume = a.take<float>((size_t)R * S);
+  w.pts = a.take<float>((size_t)R * S * 3);
+  w.raw = a.take<float>((size_t)R * S * 4);
+  const size_t m1 = mlp_workspace_bytes(cfg->precision, d_latent, (int)((size_t)R * S));
+  const size_t m2 = mlp_workspace_bytes(cfg->precision, d_latent, (int)((size_t)R * G));
+  w.mlp_ws_bytes = m1 > m2 ? m1 : m2;
+  w.mlp_ws = a.take<unsigned char>(w.mlp_ws_bytes);
+  if (out) *out = w;
+  return a.off;
+}
+
+constexpr int kDefaultLatent = 2480;
+
+}  // namespace
+
+extern "C" {
+
+int srf_abi_version(void) { return SRF_ABI_VERSION; }
+const char* srf_last_error(void) { return g_err; }
+int srf_last_launch_count(void) { return g_launches; }
+size_t srf_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(srf_config);
+    case 1: return sizeof(srf_pyramid);
+    case 2: return sizeof(srf_mlp_weights);
+    case 3: return sizeof(srf_outputs);
+    default: return 0;
+  }
+}
+
+size_t srf_pyramid_bytes(const int* C, const int* H, const int* W) {
+  size_t b = 0;
+  for (int s = 0; s < SRF_NUM_SCALES; ++s) b += align256((size_t)C[s] * H[s] * W[s] * sizeof(float));
+  return b;
+}
+
+int srf_pack_pyramid(const float* const* chw_dev, const int* C, const int* H, const int* W, void* dst_dev,
+                     size_t dst_bytes, srf_pyramid* out, void* stream) {
+  if (!chw_dev || !C || !H || !W || !dst_dev || !out) return fail(SRF_E_INVALID, "srf_pack_pyramid: NULL argument");
+  if (dst_bytes < srf_pyramid_bytes(C, H, W))
+    return fail(SRF_E_WORKSPACE, "srf_pack_pyramid: dst has %zu bytes, need %zu", dst_bytes, srf_pyramid_bytes(C, H, W));
+  unsigned char* d = reinterpret_cast<unsigned char*>(dst_dev);
+  for (int s = 0; s < SRF_NUM_SCALES; ++s) {
+    if (!chw_dev[s] || C[s] < 1 || H[s] < 1 || W[s] < 1) return fail(SRF_E_INVALID, "srf_pack_pyramid: scale %d empty", s);
+    float* dst = reinterpret_cast<float*>(d);
+    srf::launch_chw_to_hwc(chw_dev[s], dst, C[s], H[s], W[s], (cudaStream_t)stream);
+    out->hwc[s] = dst;
+    out->C[s] = C[s]; out->H[s] = H[s]; out->W[s] = W[s];
+    d += align256((size_t)C[s] * H[s] * W[s] * sizeof(float));
+  }
+  return check_cuda("srf_pack_pyramid");
+}
+
+size_t srf_tc_weights_bytes(int d_out, int d_latent) { return srf::tc_weights_bytes(d_out, d_latent); }
+
+int srf_pack_weights_tc(const srf_mlp_weights* w, void* dst_dev, size_t dst_bytes, void* stream) {
+  if (!w || !dst_dev) return fail(SRF_E_INVALID, "srf_pack_weights_tc: NULL argument");
+  if (dst_bytes < srf::tc_weights_bytes(w->d_out, w->d_latent))
+    return fail(SRF_E_WORKSPACE, "srf_pack_weights_tc: dst has %zu bytes, need %zu", dst_bytes,
+                srf::tc_weights_bytes(w->d_out, w->d_latent));
+  const int rc = srf::pack_weights_tc(*w, dst_dev, dst_bytes, (cudaStream_t)stream);
+  if (rc) return fail(SRF_E_INVALID, "srf_pack_weights_tc: unsupported shape (d_out=%d d_latent=%d)", w->d_out, w->d_latent);
+  return check_cuda("srf_pack_weights_tc");
+}
+
+size_t srf_render_workspace_bytes(const srf_config* cfg, int n_rays) {
+  if (!cfg || n_rays < 0) return 0;
+  return carve(cfg, n_rays, cfg->d_latent > 0 ? cfg->d_latent : kDefaultLatent, nullptr, nullptr) + 4096;
+}
+
+int srf_render_rays(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w_main,
+                    const srf_mlp_weights* w_gauss, const float* pixels_dev, int n_rays, const float* noise_u_dev,
+                    const float* noise_n_dev, const srf_outputs* out, void* workspace_dev, size_t workspace_bytes,
+                    void* stream) {
+  g_launches = 0;
+  if (int rc = validate(cfg, pyr)) return rc;
+  if (!pyr || !out) return fail(SRF_E_INVALID, "srf_render_rays: pyramid / outputs are NULL");
+  if (n_rays == 0) return SRF_OK;                      // empty batch: nothing to write (reference returns empty cats)
+  if (n_rays < 0 || !pixels_dev) return fail(SRF_E_INVALID, "srf_render_rays: n_rays=%d pixels=%p", n_rays, (const void*)pixels_dev);
+  const int d_latent = pyramid_channels(pyr);
+  if (int rc = validate_weights(w_main, 4, d_latent, cfg->precision)) return rc;
+  if (int rc = validate_weights(w_gauss, 2, d_latent, cfg->precision)) return rc;
+  RayWorkspace ws;
+  const size_t need = carve(cfg, n_rays, d_latent, reinterpret_cast<unsigned char*>(workspace_dev), &ws);
+  if (!workspace_dev || workspace_bytes < need)
+    return fail(SRF_E_WORKSPACE, "srf_render_rays: workspace has %zu bytes, need %zu", workspace_bytes, need);
+  const cudaStream_t st = (cudaStream_t)stream;
+  const srf::DevParams p = make_params(cfg, pyr);
+  const int R = n_rays, G = p.G, S = p.S;
+
+  srf::launch_ray_setup(p, pixels_dev, R, ws.unit, ws.viewdir, ws.gauss_pts, st);
+  ++g_launches;
+  if (int rc = check_cuda("ray_setup")) return rc;
+  if (int rc = run_mlp(p, cfg->precision, cfg->flags, *w_gauss, ws.gauss_pts, ws.viewdir, R * G, G, ws.gauss_raw,
+                       out->dbg_sphere_gauss, ws.mlp_ws, ws.mlp_ws_bytes, st))
+    return rc;
+  float* means = out->gaussian_means ? out->gaussian_means : ws.means;
+  float* stds = out->gaussian_stds ? out->gaussian_stds : ws.stds;
+  float* dv = out->depth_volumes ? out->depth_volumes : ws.depth_volume;
+  srf::launch_sample_sort(p, R, ws.unit, ws.gauss_raw, noise_u_dev, noise_n_dev, means, stds, ws.t_sorted, dv, ws.pts, st);
+  ++g_launches;
+  if (int rc = check_cuda("sample_sort")) return rc;
+  if (int rc = run_mlp(p, cfg->precision, cfg->flags, *w_main, ws.pts, ws.viewdir, R * S, S, ws.raw,
+                       out->dbg_sphere_main, ws.mlp_ws, ws.mlp_ws_bytes, st))
+    return rc;
+  srf::launch_composite_som(p, R, ws.raw, ws.t_sorted, dv, means, stds, *out, st);
+  ++g_launches;
+  return check_cuda("composite_som");
+}
+
+size_t srf_render_host_workspace_bytes(const srf_config* cfg, int n_rays) {
+  if (!cfg || n_rays < 0) return 0;
+  const size_t G = cfg->n_gaussians, S = cfg->n_pts_uni + G * cfg->n_pts_per_gaussian;
+  // staging for pixels + every output the caller may request
+  const size_t stage = align256((size_t)n_rays * 2 * 4) + 6 * align256((size_t)n_rays * 4 * 4) +
+                       3 * align256((size_t)n_rays * G * 4) + 4 * align256((size_t)n_rays * S * 4);
+  return srf_render_workspace_bytes(cfg, n_rays) + stage + 4096;
+}
+
+int srf_render_rays_host(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w_main,
+                         const srf_mlp_weights* w_gauss, const float* pixels_host, int n_rays,
+                         const srf_outputs* out_host, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!cfg || !out_host) return fail(SRF_E_INVALID, "srf_render_rays_host: NULL argument");
+  if (n_rays == 0) return SRF_OK;
+  if (n_rays < 0 || !pixels_host) return fail(SRF_E_INVALID, "srf_render_rays_host: bad rays");
+  if (!workspace_dev || workspace_bytes < srf_render_host_workspace_bytes(cfg, n_rays))
+    return fail(SRF_E_WORKSPACE, "srf_render_rays_host: workspace has %zu bytes, need %zu", workspace_bytes,
+                srf_render_host_workspace_bytes(cfg, n_rays));
+  const cudaStream_t st = (cudaStream_t)stream;
+  const size_t R = n_rays, G = cfg->n_gaussians, S = cfg->n_pts_uni + G * cfg->n_pts_per_gaussian;
+  Arena a{reinterpret_cast<unsigned char*>(workspace_dev), 0, 0};
+  float* pix = a.take<float>(R * 2);
+  srf_outputs dev;
+  memset(&dev, 0, sizeof(dev));
+  struct Item { float* const* host; float** devp; size_t count; };
+  const Item items[] = {
+      {&out_host->depth, &dev.depth, R}, {&out_host->color, &dev.color, R * 3},
+      {&out_host->gaussian_means, &dev.gaussian_means, R * G}, {&out_host->gaussian_stds, &dev.gaussian_stds, R * G},
+      {&out_host->weights_at_depth, &dev.weights_at_depth, R}, {&out_host->closest_pts_to_depths, &dev.closest_pts_to_depths, R},
+      {&out_host->loss_kl, &dev.loss_kl, R}, {&out_host->alphas, &dev.alphas, R * S},
+      {&out_host->som_vars, &dev.som_vars, R * G}, {&out_host->densities, &dev.densities, R * S},
+      {&out_host->weights, &dev.weights, R * S}, {&out_host->depth_volumes, &dev.depth_volumes, R * S},
+      {&out_host->som_means, &dev.som_means, R * G}};
+  for (const Item& it : items)
+    if (*it.host) *it.devp = a.take<float>(it.count);
+  if (cudaMemcpyAsync(pix, pixels_host, R * 2 * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return check_cuda("H2D pixels");
+  const int rc = srf_render_rays(cfg, pyr, w_main, w_gauss, pix, n_rays, nullptr, nullptr, &dev,
+                                 reinterpret_cast<unsigned char*>(workspace_dev) + a.off, workspace_bytes - a.off, stream);
+  if (rc) return rc;
+  for (const Item& it : items)
+    if (*it.host) cudaMemcpyAsync(*it.host, *it.devp, it.count * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) return check_cuda("srf_render_rays_host sync");
+  return check_cuda("srf_render_rays_host");
+}
+
+size_t srf_predict_workspace_bytes(const srf_config* cfg, int n_points) {
+  if (!cfg || n_points < 0) return 0;
+  return mlp_workspace_bytes(cfg->precision, cfg->d_latent > 0 ? cfg->d_latent : kDefaultLatent, n_points) + align256((size_t)n_points * 4 * 4) + 4096;
+}
+
+__global__ void activate_kernel(const float* __restrict__ raw, int n, float* __restrict__ density,
+                                float* __restrict__ color) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 o = reinterpret_cast<const float4*>(raw)[i];
+  if (color) {
+    color[(size_t)i * 3 + 0] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-o.x)));
+    color[(size_t)i * 3 + 1] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-o.y)));
+    color[(size_t)i * 3 + 2] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-o.z)));
+  }
+  if (density) {
+    const float x = __fsub_rn(o.w, 1.0f);
+    density[i] = (x > 20.0f) ? x : log1pf(expf(x));
+  }
+}
+
+int srf_predict(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w, const float* cam_pts_dev,
+                const float* viewdir_dev, int n_cols, int n_per, float* raw_out_dev, float* density_dev,
+                float* color_dev, int32_t* dbg_sphere_dev, void* workspace_dev, size_t workspace_bytes,
+                void* stream) {
+  g_launches = 0;
+  if (int rc = validate(cfg, pyr)) return rc;
+  if (!pyr || !w) return fail(SRF_E_INVALID, "srf_predict: NULL argument");
+  if (n_cols == 0 || n_per == 0) return SRF_OK;
+  if (n_cols < 0 || n_per < 0 || !cam_pts_dev || !viewdir_dev) return fail(SRF_E_INVALID, "srf_predict: bad points");
+  const int d_latent = pyramid_channels(pyr);
+  if (int rc = validate_weights(w, w->d_out, d_latent, cfg->precision)) return rc;
+  if (w->d_out != 2 && w->d_out != 4) return fail(SRF_E_INVALID, "srf_predict: d_out=%d", w->d_out);
+  if ((density_dev || color_dev) && w->d_out != 4)
+    return fail(SRF_E_INVALID, "srf_predict: density/color need a d_out=4 network");
+  const int n = n_cols * n_per;
+  Arena a{reinterpret_cast<unsigned char*>(workspace_dev), 0, 0};
+  float* raw = raw_out_dev ? raw_out_dev : a.take<float>((size_t)n * 4);
+  const size_t mlp_bytes = mlp_workspace_bytes(cfg->precision, d_latent, n);
+  if (!workspace_dev || workspace_bytes < a.off + mlp_bytes)
+    return fail(SRF_E_WORKSPACE, "srf_predict: workspace has %zu bytes, need %zu", workspace_bytes, a.off + mlp_bytes);
+  const srf::DevParams p = make_params(cfg, pyr);
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = run_mlp(p, cfg->precision, cfg->flags, *w, cam_pts_dev, viewdir_dev, n, n_per, raw, dbg_sphere_dev,
+                       reinterpret_cast<unsigned char*>(workspace_dev) + a.off, workspace_bytes - a.off, st))
+    return rc;
+  if (density_dev || color_dev) {
+    activate_kernel<<<(n + 255) / 256, 256, 0, st>>>(raw, n, density_dev, color_dev);
+    ++g_launches;
+  }
+  return check_cuda("srf_predict");
+}
+
+}  // extern "C"

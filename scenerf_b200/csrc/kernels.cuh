@@ -1,0 +1,35 @@
+// Host-side launchers of the scenerf_b200 kernels (definitions in the .cu files of this directory).
+#pragma once
+#include "common.cuh"
+
+namespace srf {
+
+// ray_kernels.cu
+void launch_ray_setup(const DevParams& p, const float* pixels, int R, float* unit, float* viewdir, float* gauss_pts,
+                      cudaStream_t st);
+void launch_sample_sort(const DevParams& p, int R, const float* unit, const float* gauss_raw, const float* noise_u,
+                        const float* noise_n, float* means, float* stds, float* t_sorted, float* depth_volume,
+                        float* pts, cudaStream_t st);
+void launch_composite_som(const DevParams& p, int R, const float* raw, const float* t_sorted,
+                          const float* depth_volume, const float* means, const float* stds, const srf_outputs& out,
+                          cudaStream_t st);
+
+// pack.cu
+void launch_chw_to_hwc(const float* src, float* dst, int C, int H, int W, cudaStream_t st);
+
+// mlp_simt.cu : float32 point MLP (gather + positional encoding + ResnetFC), n points in chunks.
+//   pts (n,3) infer-frame points; viewdir (n/n_per,3); raw_out (n,d_out).  Returns number of kernel launches.
+size_t simt_workspace_bytes(int d_latent, int n_points);
+int run_point_mlp_simt(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n,
+                       int n_per, float* raw_out, int32_t* dbg_sphere, void* workspace, size_t ws_bytes,
+                       cudaStream_t st);
+
+// mlp_tc.cu : tcgen05 tensor-core point MLP.
+size_t tc_weights_bytes(int d_out, int d_latent);
+int pack_weights_tc(const srf_mlp_weights& w, void* dst, size_t bytes, cudaStream_t st);
+size_t tc_workspace_bytes(int d_latent, int n_points);
+int run_point_mlp_tc(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n,
+                     int n_per, float* raw_out, int32_t* dbg_sphere, int flags, void* workspace, size_t ws_bytes,
+                     cudaStream_t st);
+
+}  // namespace srf

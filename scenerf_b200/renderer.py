@@ -1,0 +1,311 @@
+"""Host-side mirror of the reference's renderer interface on top of the C ABI.
+
+`B200Renderer.render_rays_batch` has the argument meaning and the 12-key return dict of
+`SceneRF.render_rays_batch` (/root/reference/scenerf/models/scenerf.py:392-471; BundleFusion twin
+scenerf_bf.py:420-494), `B200Renderer.predict` those of `SceneRF.predict` (scenerf.py:505-547).  `patch(model)`
+swaps the two methods of a live LightningModule for these, which is the whole integration.
+
+PyTorch is plumbing here: device memory, the current stream and (for `rng="torch"`) the reference's own RNG calls.
+All arithmetic of the path runs in libscenerf_b200.so; there is no CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import Config, MlpWeights, Outputs, Pyramid
+
+SCALE_KEYS = ("1_1", "1_2", "1_4", "1_8", "1_16")
+DICT_KEYS = ("depth", "color", "gaussian_means", "gaussian_stds", "weights_at_depth", "closest_pts_to_depths",
+             "loss_kl", "alphas", "som_vars", "densities", "weights", "depth_volumes")
+MINIMAL_KEYS = ("depth", "color")
+PRECISIONS = {"fp32": _lib.PREC_FP32, "fp16": _lib.PREC_FP16_TC}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _PackedMlp:
+    """Keeps the 22 nn.Linear tensors of a ResnetFC alive (fp32, contiguous, on device) + the tensor-core pack."""
+
+    def __init__(self, state: Dict[str, torch.Tensor], d_out: int, device, want_tc: bool):
+        lib = _lib.load()
+        g = lambda k: state[k].detach().to(device=device, dtype=torch.float32).contiguous()
+        self.tensors = {k: g(k) for k in state}
+        w = MlpWeights()
+        w.d_out = d_out
+        w.d_latent = int(self.tensors["lin_z.0.weight"].shape[1])
+        if tuple(self.tensors["lin_in.weight"].shape) != (512, 42) or self.tensors["lin_out.weight"].shape[0] != d_out:
+            raise ValueError("unexpected ResnetFC shapes: lin_in %s lin_out %s" % (
+                tuple(self.tensors["lin_in.weight"].shape), tuple(self.tensors["lin_out.weight"].shape)))
+        w.lin_in_w, w.lin_in_b = self.tensors["lin_in.weight"].data_ptr(), self.tensors["lin_in.bias"].data_ptr()
+        w.lin_out_w, w.lin_out_b = self.tensors["lin_out.weight"].data_ptr(), self.tensors["lin_out.bias"].data_ptr()
+        for b in range(3):
+            w.lin_z_w[b] = self.tensors["lin_z.%d.weight" % b].data_ptr()
+            w.lin_z_b[b] = self.tensors["lin_z.%d.bias" % b].data_ptr()
+            w.fc0_w[b] = self.tensors["blocks.%d.fc_0.weight" % b].data_ptr()
+            w.fc0_b[b] = self.tensors["blocks.%d.fc_0.bias" % b].data_ptr()
+            w.fc1_w[b] = self.tensors["blocks.%d.fc_1.weight" % b].data_ptr()
+            w.fc1_b[b] = self.tensors["blocks.%d.fc_1.bias" % b].data_ptr()
+        self.packed = None
+        if want_tc:
+            nbytes = lib.srf_tc_weights_bytes(d_out, w.d_latent)
+            self.packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            _lib.check(lib.srf_pack_weights_tc(C.byref(w), _ptr(self.packed), nbytes, _stream_ptr(device)))
+            w.tc_packed = self.packed.data_ptr()
+        self.struct = w
+
+
+class B200Renderer:
+    """Drop-in for the renderer half of SceneRF (scenerf.py:392-748) on one B200.
+
+    hp: dict with the module attributes the path reads -- dataset ("kitti"|"bf"), n_pts_uni, n_gaussians,
+        n_pts_per_gaussian, std, max_sample_depth, out_img_W, out_img_H, som_sigma, v_angle_min/max,
+        h_angle_min/max (SphericalMapping incl. add_fov).
+    mlp_state / mlp_gaussian_state: ResnetFC state dicts (resnetfc.py parameter names).
+    precision: "fp16" tensor cores (tcgen05, fp32 accumulate) or "fp32" strict SIMT.
+    rng: "torch" reproduces the reference's two RNG calls (utils.py:84, 208-211) chunk by chunk so that seeded runs
+         see identical noise; "philox" draws in-kernel (no noise tensors, fastest).
+    """
+
+    def __init__(self, hp: dict, mlp_state, mlp_gaussian_state, device="cuda:0", precision: str = "fp16",
+                 rng: str = "philox", skip_zero_chunks: bool = False):
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % list(PRECISIONS))
+        if rng not in ("torch", "philox"):
+            raise ValueError("rng must be 'torch' or 'philox'")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("scenerf_b200 needs a CUDA device (no CPU fallback); got %s" % device)
+        self.hp = dict(hp)
+        self.precision = precision
+        self.rng = rng
+        self.skip_zero_chunks = skip_zero_chunks
+        want_tc = precision == "fp16"
+        self.mlp = _PackedMlp(mlp_state, 4, self.device, want_tc)
+        self.mlp_gaussian = _PackedMlp(mlp_gaussian_state, 2, self.device, want_tc)
+        self._pyr_key = None
+        self._pyr_buf = None
+        self._pyr = None
+        self._ws = None
+        self.seed = 0x5CE9E2F
+        self.last_launches = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_module(cls, model, **kw):
+        """Build from a live reference LightningModule (scenerf.py:22 / scenerf_bf.py:27)."""
+        sm = model.spherical_mapping
+        dataset = "bf" if type(model).__module__.endswith("scenerf_bf") else "kitti"
+        hp = dict(dataset=dataset, n_pts_uni=model.n_pts_uni, n_gaussians=model.n_gaussians,
+                  n_pts_per_gaussian=model.n_pts_per_gaussian, std=model.std,
+                  max_sample_depth=model.max_sample_depth, out_img_W=model.out_img_W, out_img_H=model.out_img_H,
+                  som_sigma=model.ray_som.som_sigma, v_angle_min=sm.v_angle_min, v_angle_max=sm.v_angle_max,
+                  h_angle_min=sm.h_angle_min, h_angle_max=sm.h_angle_max)
+        device = kw.pop("device", None) or next(model.mlp.parameters()).device
+        return cls(hp, model.mlp.state_dict(), model.mlp_gaussian.state_dict(), device=device, **kw)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _pack_pyramid(self, x_rgb: Dict[str, torch.Tensor]):
+        ts = [x_rgb[k] for k in SCALE_KEYS]
+        key = tuple((t.data_ptr(), tuple(t.shape), t._version) for t in ts)
+        if key == self._pyr_key:
+            return self._pyr
+        src = []
+        for t in ts:
+            if t.dim() != 3:
+                raise ValueError("x_rgb maps must be unbatched CHW (scenerf.py:154-156), got %s" % (tuple(t.shape),))
+            src.append(t.detach().to(device=self.device, dtype=torch.float32).contiguous())
+        Cs = (C.c_int * 5)(*[t.shape[0] for t in src])
+        Hs = (C.c_int * 5)(*[t.shape[1] for t in src])
+        Ws = (C.c_int * 5)(*[t.shape[2] for t in src])
+        nbytes = self.lib.srf_pyramid_bytes(Cs, Hs, Ws)
+        if self._pyr_buf is None or self._pyr_buf.numel() < nbytes:
+            self._pyr_buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        ptrs = (C.c_void_p * 5)(*[t.data_ptr() for t in src])
+        pyr = Pyramid()
+        _lib.check(self.lib.srf_pack_pyramid(ptrs, Cs, Hs, Ws, _ptr(self._pyr_buf), nbytes, C.byref(pyr),
+                                             _stream_ptr(self.device)))
+        self._pyr, self._pyr_key = pyr, key
+        self._pyr_src = src          # keep sources alive until the async pack has certainly run
+        return pyr
+
+    def _config(self, cam_K: torch.Tensor, T: Optional[torch.Tensor]) -> Config:
+        hp = self.hp
+        cfg = Config()
+        cfg.dataset = 0 if hp["dataset"] == "kitti" else 1
+        n_uni = int(hp["n_pts_uni"])
+        if hp["dataset"] == "bf" and n_uni <= 0:
+            n_uni = 2                                    # scenerf_bf.py:623-626
+        cfg.n_pts_uni = n_uni
+        cfg.n_gaussians = int(hp["n_gaussians"])
+        cfg.n_pts_per_gaussian = int(hp["n_pts_per_gaussian"])
+        cfg.max_sample_depth = float(hp["max_sample_depth"])
+        cfg.base_std = float(hp["std"])
+        cfg.som_sigma = float(hp["som_sigma"])
+        cfg.sphere_W, cfg.sphere_H = int(hp["out_img_W"]), int(hp["out_img_H"])
+        cfg.d_latent = int(self.mlp.struct.d_latent)
+        cfg.v_angle_min, cfg.v_angle_max = float(hp["v_angle_min"]), float(hp["v_angle_max"])
+        cfg.h_angle_min, cfg.h_angle_max = float(hp["h_angle_min"]), float(hp["h_angle_max"])
+        K = cam_K.detach().to(torch.float32)
+        inv_K = torch.inverse(K)                         # same op as scenerf.py:401 -> bit-equal inverse
+        cfg.K = (C.c_float * 9)(*K.reshape(-1).tolist())
+        cfg.inv_K = (C.c_float * 9)(*inv_K.reshape(-1).tolist())
+        if T is None:
+            T = torch.eye(4)
+        cfg.T = (C.c_float * 16)(*T.detach().to(torch.float32).reshape(-1).tolist())
+        cfg.precision = PRECISIONS[self.precision]
+        cfg.seed = self.seed
+        cfg.flags = _lib.FLAG_SKIP_ZERO_CHUNKS if self.skip_zero_chunks else 0
+        return cfg
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _draw_noise_like_reference(self, R: int, ray_batch_size: int, cfg: Config):
+        """The reference draws, per ray chunk, torch.rand_like on an expanded (R_c,U,1) device tensor (utils.py:78-84)
+        and then torch.normal on the CPU (utils.py:208-211).  Same calls, same order -> same streams."""
+        U, GP = cfg.n_pts_uni, cfg.n_gaussians * cfg.n_pts_per_gaussian
+        us, ns = [], []
+        for s in range(0, R, ray_batch_size):
+            rc = min(ray_batch_size, R - s)
+            lin = torch.linspace(0.2, cfg.max_sample_depth, steps=U, device=self.device).reshape(1, U, 1).expand(rc, -1, -1)
+            us.append(torch.rand_like(lin).reshape(rc, U))
+            ns.append(torch.normal(mean=torch.zeros(rc, GP), std=torch.ones(rc, GP)).to(self.device))
+        return torch.cat(us, 0).contiguous(), torch.cat(ns, 0).contiguous()
+
+    # ------------------------------------------------------------------------------------------------------------
+    def render_rays_batch(self, cam_K, T_source2infer, x_rgb, depth_window=100, T_cam2velo=None,
+                          sampled_pixels=None, ray_batch_size=128, *, noise=None, outputs="all", debug=False):
+        """scenerf.py:392-471.  `depth_window` and `T_cam2velo` are accepted and unused, exactly like the reference.
+        noise: optional (noise_u (R,U), noise_n (R,G*P)) tensors overriding the RNG (parity tests).
+        outputs: "all" -> the reference's 12-key dict; "minimal" -> depth and color only (what inference reads)."""
+        if sampled_pixels is None:
+            raise TypeError("sampled_pixels is required (the reference fails on None too: scenerf.py:419)")
+        pix = sampled_pixels.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        if pix.dim() != 2 or pix.shape[1] != 2:
+            raise ValueError("sampled_pixels must be (R,2), got %s" % (tuple(pix.shape),))
+        R = int(pix.shape[0])
+        cfg = self._config(cam_K, T_source2infer)
+        pyr = self._pack_pyramid(x_rgb)
+        G, S = cfg.n_gaussians, cfg.n_pts_uni + cfg.n_gaussians * cfg.n_pts_per_gaussian
+        keys = DICT_KEYS if outputs == "all" else MINIMAL_KEYS
+        shapes = dict(depth=(R,), color=(R, 3), gaussian_means=(R, G), gaussian_stds=(R, G), weights_at_depth=(R,),
+                      closest_pts_to_depths=(R,), loss_kl=(R,), alphas=(R, S), som_vars=(R, G), densities=(R, S),
+                      weights=(R, S), depth_volumes=(R, S))
+        ret = {k: torch.empty(shapes[k], dtype=torch.float32, device=self.device) for k in keys}
+        out = Outputs()
+        for k in keys:
+            setattr(out, k, ret[k].data_ptr())
+        if debug:
+            ret["som_means"] = torch.empty((R, G), dtype=torch.float32, device=self.device)
+            ret["dbg_sphere_main"] = torch.empty((R * S, 2), dtype=torch.int32, device=self.device)
+            ret["dbg_sphere_gauss"] = torch.empty((R * G, 2), dtype=torch.int32, device=self.device)
+            for k in ("som_means", "dbg_sphere_main", "dbg_sphere_gauss"):
+                setattr(out, k, ret[k].data_ptr())
+        if R == 0:
+            return ret
+        nu = nn_ = None
+        if noise is not None:
+            nu = noise[0].detach().to(device=self.device, dtype=torch.float32).contiguous()
+            nn_ = noise[1].detach().to(device=self.device, dtype=torch.float32).contiguous()
+            if tuple(nu.shape) != (R, cfg.n_pts_uni) or tuple(nn_.shape) != (R, G * cfg.n_pts_per_gaussian):
+                raise ValueError("noise shapes %s %s" % (tuple(nu.shape), tuple(nn_.shape)))
+        elif self.rng == "torch":
+            nu, nn_ = self._draw_noise_like_reference(R, int(ray_batch_size), cfg)
+        else:
+            self.seed += 1
+            cfg.seed = self.seed
+        nbytes = self.lib.srf_render_workspace_bytes(C.byref(cfg), R)
+        ws = self._workspace(nbytes)
+        _lib.check(self.lib.srf_render_rays(C.byref(cfg), C.byref(pyr), C.byref(self.mlp.struct),
+                                            C.byref(self.mlp_gaussian.struct), _ptr(pix), R, _ptr(nu), _ptr(nn_),
+                                            C.byref(out), _ptr(ws), ws.numel(), _stream_ptr(self.device)))
+        self.last_launches = self.lib.srf_last_launch_count()
+        return ret
+
+    # ------------------------------------------------------------------------------------------------------------
+    def predict(self, mlp, cam_pts, x_rgb, cam_K, T_cam2velo=None, viewdir=None, output_type="density", *,
+                debug=False):
+        """scenerf.py:505-547.  `mlp` selects the network: the string "mlp"/"mlp_gaussian", or one of this
+        renderer's packed networks, or the nn.Module the renderer was built from (matched by d_out)."""
+        if viewdir is None:
+            raise TypeError("viewdir is required (scenerf.py:508)")
+        net = self._select(mlp)
+        pts = cam_pts.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        saved = tuple(pts.shape)
+        if pts.dim() != 3 or saved[2] != 3:
+            raise ValueError("cam_pts must be (n_cols, n_per, 3), got %s" % (saved,))
+        vd = viewdir.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        n_cols, n_per = saved[0], saved[1]
+        cfg = self._config(cam_K, None)
+        pyr = self._pack_pyramid(x_rgb)
+        n = n_cols * n_per
+        d_out = net.struct.d_out
+        raw = torch.empty((n, d_out), dtype=torch.float32, device=self.device)
+        dens = col = None
+        if output_type == "density":
+            if d_out != 4:
+                raise ValueError("output_type='density' needs the d_out=4 network")
+            dens = torch.empty((n_cols, n_per), dtype=torch.float32, device=self.device)
+            col = torch.empty((n_cols, n_per, 3), dtype=torch.float32, device=self.device)
+        dbg = torch.empty((n, 2), dtype=torch.int32, device=self.device) if debug else None
+        if n:
+            nbytes = self.lib.srf_predict_workspace_bytes(C.byref(cfg), n)
+            ws = self._workspace(nbytes)
+            _lib.check(self.lib.srf_predict(C.byref(cfg), C.byref(pyr), C.byref(net.struct), _ptr(pts), _ptr(vd),
+                                            n_cols, n_per, _ptr(raw), _ptr(dens), _ptr(col), _ptr(dbg), _ptr(ws),
+                                            ws.numel(), _stream_ptr(self.device)))
+            self.last_launches = self.lib.srf_last_launch_count()
+        if output_type == "density":
+            return (dens, col, dbg) if debug else (dens, col)
+        res = raw.reshape(n_cols, n_per, d_out)
+        return (res, dbg) if debug else res
+
+    def _select(self, mlp):
+        if mlp in ("mlp", None) or mlp is self.mlp:
+            return self.mlp
+        if mlp in ("mlp_gaussian",) or mlp is self.mlp_gaussian:
+            return self.mlp_gaussian
+        d_out = getattr(mlp, "d_out", None)
+        if d_out == 4:
+            return self.mlp
+        if d_out == 2:
+            return self.mlp_gaussian
+        raise ValueError("cannot map %r to mlp / mlp_gaussian" % (mlp,))
+
+
+def patch(model, **kw):
+    """Replace `model.render_rays_batch` / `model.predict` of a reference SceneRF module by the B200 path.
+    Call again after loading new weights.  Returns the renderer."""
+    r = B200Renderer.from_module(model, **kw)
+    if r.hp["dataset"] == "kitti":
+        def render_rays_batch(cam_K, T_source2infer, x_rgb, depth_window=100, T_cam2velo=None, sampled_pixels=None,
+                              ray_batch_size=128):
+            return r.render_rays_batch(cam_K, T_source2infer, x_rgb, depth_window, T_cam2velo, sampled_pixels,
+                                       ray_batch_size)
+
+        def predict(mlp, cam_pts, x_rgb, cam_K, T_cam2velo, viewdir, output_type="density"):
+            return r.predict(mlp, cam_pts, x_rgb, cam_K, T_cam2velo, viewdir, output_type)
+    else:
+        def render_rays_batch(cam_K, T_source2infer, x_rgb, sampled_pixels=None, ray_batch_size=128):
+            return r.render_rays_batch(cam_K, T_source2infer, x_rgb, sampled_pixels=sampled_pixels,
+                                       ray_batch_size=ray_batch_size)
+
+        def predict(mlp, cam_pts, x_rgb, cam_K, viewdir, output_type="density"):
+            return r.predict(mlp, cam_pts, x_rgb, cam_K, None, viewdir, output_type)
+    model.render_rays_batch = render_rays_batch
+    model.predict = predict
+    model._b200_renderer = r
+    return r
