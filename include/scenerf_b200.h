@@ -159,6 +159,14 @@ int srf_predict(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_wei
                 float* color_dev, int32_t* dbg_sphere_dev, void* workspace_dev, size_t workspace_bytes,
                 void* stream);
 
+/* Diagnostic (not part of the reference-facing surface): run the tensor-core point MLP of srf_predict but stop each
+ * 128-point tile after layer `layer` of the tile program (mlp_tc.cu: 1 lin_in+lin_z0, 2 fc0_0, 4 fc1_0+lin_z1,
+ * 5 fc0_1, 7 fc1_1+lin_z2, 8 fc0_2, 9 fc1_2, 10 lin_out) and write the raw fp32 accumulator rows to
+ * acc_out_dev (ceil(n/128)*128, 512). */
+int srf_debug_tc_layer(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w,
+                       const float* cam_pts_dev, const float* viewdir_dev, int n_cols, int n_per, int layer,
+                       float* acc_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Number of kernels the last srf_render_rays / srf_predict call on this thread launched (bench "gpu_launches"). */
 int srf_last_launch_count(void);
 

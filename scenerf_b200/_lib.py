@@ -76,6 +76,9 @@ SYMBOLS = {
     "srf_predict": (C.c_int, [C.POINTER(Config), C.POINTER(Pyramid), C.POINTER(MlpWeights), C.c_void_p, C.c_void_p,
                               C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_size_t, C.c_void_p]),
+    "srf_debug_tc_layer": (C.c_int, [C.POINTER(Config), C.POINTER(Pyramid), C.POINTER(MlpWeights), C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                     C.c_void_p]),
 }
 
 _lib = None

@@ -376,4 +376,23 @@ int srf_predict(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_wei
   return check_cuda("srf_predict");
 }
 
+int srf_debug_tc_layer(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w,
+                       const float* cam_pts_dev, const float* viewdir_dev, int n_cols, int n_per, int layer,
+                       float* acc_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  if (int rc = validate(cfg, pyr)) return rc;
+  if (!pyr || !w || !cam_pts_dev || !viewdir_dev || !acc_out_dev || n_cols < 1 || n_per < 1)
+    return fail(SRF_E_INVALID, "srf_debug_tc_layer: bad argument");
+  const int d_latent = pyramid_channels(pyr);
+  if (int rc = validate_weights(w, w->d_out, d_latent, SRF_PREC_FP16_TC)) return rc;
+  const srf::DevParams p = make_params(cfg, pyr);
+  const int l = srf::run_point_mlp_tc_debug(p, *w, cam_pts_dev, viewdir_dev, n_cols * n_per, n_per, nullptr, nullptr,
+                                            cfg->flags, workspace_dev, workspace_bytes, layer, acc_out_dev,
+                                            (cudaStream_t)stream);
+  if (l == -1) return fail(SRF_E_WORKSPACE, "srf_debug_tc_layer: workspace too small");
+  if (l < 0) return fail(SRF_E_INVALID, "srf_debug_tc_layer: layer %d has no accumulator-complete point", layer);
+  g_launches += l;
+  return check_cuda("srf_debug_tc_layer");
+}
+
 }  // extern "C"

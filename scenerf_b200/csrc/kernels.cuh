@@ -32,4 +32,10 @@ int run_point_mlp_tc(const DevParams& p, const srf_mlp_weights& w, const float* 
                      int n_per, float* raw_out, int32_t* dbg_sphere, int flags, void* workspace, size_t ws_bytes,
                      cudaStream_t st);
 
+// diagnostic: stop every tile after `debug_layer` (1,2,4,5,7,8,9,10 -- see the tile program in mlp_tc.cu) and dump the
+// raw fp32 accumulator (n_tiles*128, 512) to debug_acc
+int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n,
+                           int n_per, float* raw_out, int32_t* dbg_sphere, int flags, void* workspace, size_t ws_bytes,
+                           int debug_layer, float* debug_acc, cudaStream_t st);
+
 }  // namespace srf

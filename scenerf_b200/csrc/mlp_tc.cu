@@ -1,9 +1,749 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// Fused point-MLP on Blackwell tensor cores (sm_100a): one persistent, warp-specialised kernel does, per 128-point
+// tile, projection -> integer sphere coords -> positional encoding -> 5-scale bilinear gather -> the whole ResnetFC
+// (lin_in, 3 x [lin_z, fc_0, fc_1], lin_out) with tcgen05.mma (fp16 operands, fp32 accumulators in TMEM).  The
+// (N x 2522) x_in matrix of the reference (scenerf/models/scenerf.py:527-531) and all hidden activations never touch
+// HBM: gathered features / activations are produced straight into 128B-swizzled shared-memory A tiles, weights are
+// streamed as pre-swizzled stage images by cp.async.bulk (TMA engine, UBLKCP) through an mbarrier ring.
+//
+// Reference computed here: scenerf.py:505-531 (predict up to mlp(x_in)), resnetfc.py:54-63,133-164.
+//
+// Tile program (A-chunk = 128 rows x 64 k, fp16, K-major SW128; each A chunk meets 4 B images of 128 rows(N) x 64 k):
+//   L0  lin_in   1 chunk   fresh   ACC  = x Win^T
+//   L1  lin_z0   KZ chunks acc     ACC += z Wz0^T                  -> E1: h = ACC + c0            ; A = relu(h)
+//   L2  fc_0     8 chunks  fresh   ACC  = relu(h) W0^T             -> E2: net = ACC + b0          ; A = relu(net)
+//   L3  fc_1     8 chunks  fresh   ACC  = relu(net) W1^T
+//   L4  lin_z1   KZ        acc     ACC += z Wz1^T                  -> E1: h = h + ACC + c1 ...
+//   ... (blocks 1, 2) ...
+//   L9  fc_1     8         fresh                                   -> E3: h = h + ACC + b1_2      ; A = relu(h)
+//   L10 lin_out  8 (N=16)  fresh   ACC[:, :16] = relu(h) Wout^T    -> E4: out = ACC + bout
+// The fp32 hidden state h (128 x 512) cannot share the 512 TMEM columns with the accumulator of the next layer, so
+// it lives in a per-CTA 256 KB scratch that stays L2-resident (9 B/cycle/SM of traffic); biases are folded into the
+// epilogues as cumulative vectors c_b.
+//
+// Warp roles (320 threads, 1 CTA / SM):  warp 0 = weight producer (bulk copies), warp 1 = MMA issuer + TMEM owner,
+// warps 2..9 = 256 workers: geometry front-end, A-chunk producers (gather / activations) and TMEM epilogues.
+#include <cuda_fp16.h>
 #include "kernels.cuh"
+
 namespace srf {
-size_t tc_weights_bytes(int, int) { return 256; }
-int pack_weights_tc(const srf_mlp_weights&, void*, size_t, cudaStream_t) { return 1; }
-size_t tc_workspace_bytes(int, int) { return 256; }
-int run_point_mlp_tc(const DevParams&, const srf_mlp_weights&, const float*, const float*, int, int, float*, int32_t*,
-                     int, void*, size_t, cudaStream_t) { return -1; }
+namespace tc {
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;                       // fp16 elements per A/B row = 128 bytes = one SW128 atom row
+constexpr int kASlots = 8, kASlotBytes = kTileM * 128;          // 16 KB
+constexpr int kBSlots = 6, kBRows = 128, kBSlotBytes = kBRows * 128;   // 16 KB
+constexpr int kHiddenChunks = kHidden / kChunkK;  // 8
+constexpr int kQuarters = kHidden / kBRows;       // 4 N-quarters of 128
+constexpr int kOutN = 16;                         // lin_out padded to the minimum UMMA N for M=128
+constexpr int kOutImgBytes = kOutN * 128;         // 2 KB
+constexpr int kWorkerWarps = 8, kWorkerThreads = kWorkerWarps * 32;
+constexpr int kThreads = 64 + kWorkerThreads;     // 320
+constexpr int kTmemCols = 512;
+constexpr int kNumBias = 8;                       // c0,c1,c2, b_fc0[0..2], b_fc1_2, b_out(padded)
+constexpr size_t kHeaderBytes = (size_t)kNumBias * kHidden * sizeof(float);   // 16 KB
+constexpr int kNumLayers = 11;
+
+// dynamic shared memory carve-up
+constexpr int kSmemA = 0;
+constexpr int kSmemB = kSmemA + kASlots * kASlotBytes;                 // 131072
+constexpr int kSmemBar = kSmemB + kBSlots * kBSlotBytes;               // 229376
+constexpr int kNumBars = 2 * kASlots + 2 * kBSlots + 2;                // a_full/empty, b_full/empty, acc_full, meta
+constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
+constexpr int kSmemMask = kSmemTmemPtr + 8;                            // 2 x uint64 active-chunk masks (double buffer)
+constexpr int kSmemSph = kSmemMask + 16;                               // int2 sx,sy per row: 1 KB
+constexpr int kSmemTotal = kSmemSph + kTileM * 8;
+static_assert(kSmemTotal + 1024 <= 232448, "shared memory budget");
+
+struct Layer { int chunks_is_kz, chunks, fresh, signal, is_out; };
+// chunks_is_kz: number of chunks = KZ (runtime) instead of `chunks`
+__constant__ Layer kLayers[kNumLayers] = {
+    {0, 1, 1, 0, 0}, {1, 0, 0, 1, 0},                       // lin_in, lin_z0
+    {0, 8, 1, 1, 0}, {0, 8, 1, 0, 0}, {1, 0, 0, 1, 0},      // fc0_0, fc1_0, lin_z1
+    {0, 8, 1, 1, 0}, {0, 8, 1, 0, 0}, {1, 0, 0, 1, 0},      // fc0_1, fc1_1, lin_z2
+    {0, 8, 1, 1, 0}, {0, 8, 1, 1, 0},                       // fc0_2, fc1_2
+    {0, 8, 1, 1, 1}};                                       // lin_out
+
+struct KernelArgs {
+  const float* pts;        // (n,3)
+  const float* viewdir;    // (n/n_per,3)
+  int n, n_per, n_tiles, kz;
+  const unsigned char* wblob;   // header (biases) + stage images
+  float* scratch;          // gridDim.x * 128*512 floats
+  float* raw_out;          // (n, d_out)
+  int d_out;
+  int32_t* dbg_sphere;     // (n,2) or null
+  int skip_zero;           // SRF_FLAG_SKIP_ZERO_CHUNKS
+  int debug_layer;         // -1, or: stop every tile after this layer's ACC is complete and dump it
+  float* debug_acc;        // (n_tiles*128, 512)
+  int* error_flag;         // set to non-zero by the watchdog
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU -- after ~2 s the watchdog records the barrier and traps.
+__device__ __noinline__ void mbar_timeout(int* error_flag, uint32_t bar, uint32_t parity) {
+  if (error_flag) atomicExch(error_flag, (int)(0x40000000u | ((bar & 0xFFFFF) << 4) | (parity & 1) | ((threadIdx.x >> 5) << 24)));
+  __threadfence_system();
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) mbar_timeout(error_flag, bar, parity);
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; kind::f16, single-CTA
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): start address >> 4 in
+// bits [0,14), leading byte offset (unused for swizzled K-major, =1) in [16,30), stride byte offset (1024 B between
+// 8-row core groups) in [32,46), descriptor version 1 in [46,48), layout type 2 (SWIZZLE_128B) in [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format F16 (0) at [7,10) and
+// [10,13), a/b K-major (0) at 15/16, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of (row, 16-byte granule g) inside a 128B-swizzled K-major tile whose rows are 128 bytes
+__device__ __forceinline__ uint32_t sw128_offset(int row, int g) { return (uint32_t)(row * 128 + ((g ^ (row & 7)) << 4)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ring bookkeeping shared by all roles (every role walks the same program, so (slot, parity) stay in lock-step).
+// ---------------------------------------------------------------------------------------------------------------
+struct Ring {
+  int slot = 0;
+  uint32_t phase = 0;
+  template <int N>
+  __device__ __forceinline__ void advance() {
+    if (++slot == N) { slot = 0; phase ^= 1; }
+  }
+};
+
+__device__ __forceinline__ int layer_chunks(int l, int kz) { return kLayers[l].chunks_is_kz ? kz : kLayers[l].chunks; }
+// chunk c of a lin_z layer is active for this tile?  (mask bit c; all ones when skipping is off)
+__device__ __forceinline__ bool chunk_active(int l, int c, uint64_t mask) { return !kLayers[l].chunks_is_kz || ((mask >> c) & 1ull); }
+
+// which pyramid scales touch K-chunk c (channels [64c, 64c+64))
+__device__ __forceinline__ uint64_t chunk_mask_for_scales(const DevParams& p, uint32_t scale_bits, int kz) {
+  uint64_t m = 0;
+  for (int c = 0; c < kz; ++c) {
+    const int lo = c * kChunkK, hi = lo + kChunkK;
+    for (int s = 0; s < kScales; ++s)
+      if (((scale_bits >> s) & 1u) && p.ch_off[s] < hi && p.ch_off[s + 1] > lo) m |= 1ull << c;
+  }
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__ KernelArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack for this round-up
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_base + kSmemBar;
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (kASlots + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * kASlots + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * kASlots + kBSlots + s); };
+  const uint32_t acc_full = bar0 + 8u * (2 * kASlots + 2 * kBSlots);
+  const uint32_t meta_full = acc_full + 8u;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
+  volatile unsigned long long* mask_smem = reinterpret_cast<volatile unsigned long long*>(smem + kSmemMask);
+  int2* sph_smem = reinterpret_cast<int2*>(smem + kSmemSph);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kASlots; ++s) { mbar_init(a_full(s), kWorkerWarps); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kBSlots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(meta_full, kWorkerWarps);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_base + kSmemTmemPtr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int kz = a.kz;
+  const int last_layer = (a.debug_layer >= 0) ? a.debug_layer : (kNumLayers - 1);
+  const unsigned char* images = a.wblob + kHeaderBytes;
+
+  if (warp == 0) {
+    // ===================================== weight producer =====================================================
+    if (lane == 0) {
+      Ring rb;
+      uint32_t meta_phase = 0;
+      for (int tile = blockIdx.x, it = 0; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        uint64_t mask = ~0ull;
+        bool have_mask = !a.skip_zero;
+        size_t off = 0;
+        for (int l = 0; l <= last_layer; ++l) {
+          const int nc = layer_chunks(l, kz);
+          const bool is_out = kLayers[l].is_out;
+          if (kLayers[l].chunks_is_kz && !have_mask) {
+            mbar_wait(meta_full, meta_phase, a.error_flag);        // workers published this tile's chunk mask
+            mask = mask_smem[it & 1];
+            have_mask = true;
+          }
+          for (int c = 0; c < nc; ++c) {
+            const int nimg = is_out ? 1 : kQuarters;
+            const uint32_t bytes = is_out ? kOutImgBytes : kBSlotBytes;
+            if (chunk_active(l, c, mask)) {
+              for (int q = 0; q < nimg; ++q) {
+                mbar_wait(b_empty(rb.slot), rb.phase ^ 1, a.error_flag);
+                mbar_arrive_expect_tx(b_full(rb.slot), bytes);
+                bulk_g2s(smem_base + kSmemB + rb.slot * kBSlotBytes, images + off + (size_t)q * bytes, bytes, b_full(rb.slot));
+                rb.advance<kBSlots>();
+              }
+            }
+            off += (size_t)nimg * bytes;
+          }
+        }
+        if (a.skip_zero) meta_phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ==========================================================
+    if (lane == 0) {
+      Ring ra, rb;
+      uint32_t meta_phase = 0;
+      const uint32_t idesc_main = make_idesc(kTileM, kBRows);
+      const uint32_t idesc_out = make_idesc(kTileM, kOutN);
+      for (int tile = blockIdx.x, it = 0; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        uint64_t mask = ~0ull;
+        bool have_mask = !a.skip_zero;
+        for (int l = 0; l <= last_layer; ++l) {
+          const int nc = layer_chunks(l, kz);
+          const bool is_out = kLayers[l].is_out;
+          if (kLayers[l].chunks_is_kz && !have_mask) {
+            mbar_wait(meta_full, meta_phase, a.error_flag);
+            mask = mask_smem[it & 1];
+            have_mask = true;
+          }
+          bool first = kLayers[l].fresh;           // the first executed chunk of a fresh layer overwrites ACC
+          for (int c = 0; c < nc; ++c) {
+            if (!chunk_active(l, c, mask)) continue;
+            mbar_wait(a_full(ra.slot), ra.phase, a.error_flag);
+            tc_fence_after();
+            const uint64_t adesc = make_desc_sw128(smem_base + kSmemA + ra.slot * kASlotBytes);
+            const int nq = is_out ? 1 : kQuarters;
+            for (int q = 0; q < nq; ++q) {
+              mbar_wait(b_full(rb.slot), rb.phase, a.error_flag);
+              tc_fence_after();
+              const uint64_t bdesc = make_desc_sw128(smem_base + kSmemB + rb.slot * kBSlotBytes);
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k) {
+                // +32 bytes per UMMA_K=16 fp16 inside the swizzle atom row: start address field += 2
+                umma_f16(tmem_base + (uint32_t)(q * kBRows), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                         is_out ? idesc_out : idesc_main, (first && k == 0) ? 0u : 1u);
+              }
+              umma_commit(b_empty(rb.slot));
+              rb.advance<kBSlots>();
+            }
+            first = false;
+            umma_commit(a_empty(ra.slot));
+            ra.advance<kASlots>();
+          }
+          if (kLayers[l].signal || l == last_layer) umma_commit(acc_full);
+        }
+        if (a.skip_zero) meta_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================================== workers =============================================================
+    const int wt = threadIdx.x - 64;             // 0..255
+    const int q4 = warp & 3;                     // TMEM lane quarter this warp may access
+    const int col_half = (warp >= 6) ? 1 : 0;    // warps (2,6),(3,7),(4,8),(5,9) share a quarter
+    const int erow = q4 * 32 + lane;             // epilogue row
+    const float* bias = reinterpret_cast<const float*>(a.wblob);
+    float4* scratch4 = reinterpret_cast<float4*>(a.scratch + (size_t)blockIdx.x * kTileM * kHidden);
+    Ring ra;
+    uint32_t acc_phase = 0;
+
+    // -- helpers -------------------------------------------------------------------------------------------
+    auto publish_chunk = [&]() {                 // all of this warp's writes to the current A slot are done
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(ra.slot));
+      ra.advance<kASlots>();
+    };
+    auto wait_slot = [&]() { mbar_wait(a_empty(ra.slot), ra.phase ^ 1, a.error_flag); };
+
+    for (int tile = blockIdx.x, it = 0; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int row0 = tile * kTileM;
+      // ---------------- front-end: geometry of this tile's 128 points (threads 0..127, one point each) --------
+      float px = 0.f, py = 0.f, pz = 0.f;
+      uint32_t my_scales = 0;
+      if (wt < kTileM) {
+        const int gi = row0 + wt;
+        int sx = kSphereInvalid, sy = kSphereInvalid;
+        if (gi < a.n) {
+          px = a.pts[(size_t)gi * 3 + 0]; py = a.pts[(size_t)gi * 3 + 1]; pz = a.pts[(size_t)gi * 3 + 2];
+          point_to_sphere(p, px, py, pz, sx, sy);
+          if (a.dbg_sphere) { a.dbg_sphere[(size_t)gi * 2 + 0] = sx; a.dbg_sphere[(size_t)gi * 2 + 1] = sy; }
+        }
+        sph_smem[wt] = make_int2(sx, sy);
+        if (a.skip_zero) {
+#pragma unroll
+          for (int s = 0; s < kScales; ++s) my_scales |= scale_taps(p, s, sx, sy).any ? (1u << s) : 0u;
+        }
+      }
+      if (a.skip_zero) {
+        // OR the per-point scale bits over the tile -> chunk mask (one atomicOr per warp)
+        uint32_t wbits = __reduce_or_sync(0xffffffffu, my_scales);
+        if (wt == 0) mask_smem[it & 1] = 0ull;
+        named_bar_sync(1, kWorkerThreads);
+        if (lane == 0 && wbits) atomicOr((unsigned long long*)&mask_smem[it & 1], chunk_mask_for_scales(p, wbits, kz));
+      }
+      named_bar_sync(1, kWorkerThreads);          // sph_smem (and the mask) visible to all workers
+      uint64_t mask = ~0ull;
+      if (a.skip_zero) {
+        mask = mask_smem[it & 1];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(meta_full);    // release: producer + MMA issuer may read the mask
+      }
+
+      // ---------------- L0: x chunk = [pe(39) | viewdir(3) | 0] as fp16 ---------------------------------------
+      wait_slot();
+      if (wt < kTileM) {
+        float xv[kChunkK];
+#pragma unroll
+        for (int k = 0; k < kChunkK; ++k) xv[k] = 0.0f;
+        const int gi = row0 + wt;
+        if (gi < a.n) {
+          positional_encoding(px, py, pz, [&](int k, float v) { xv[k] = v; });
+          const float* vd = a.viewdir + (size_t)(gi / a.n_per) * 3;
+          xv[kDPE + 0] = vd[0]; xv[kDPE + 1] = vd[1]; xv[kDPE + 2] = vd[2];
+        }
+        const uint32_t slot_addr = smem_base + kSmemA + ra.slot * kASlotBytes;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          sts128(slot_addr + sw128_offset(wt, g), pack_half2(xv[8 * g + 0], xv[8 * g + 1]), pack_half2(xv[8 * g + 2], xv[8 * g + 3]),
+                 pack_half2(xv[8 * g + 4], xv[8 * g + 5]), pack_half2(xv[8 * g + 6], xv[8 * g + 7]));
+      }
+      publish_chunk();
+
+      // ---------------- gather pass: produces the KZ latent chunks of one lin_z layer --------------------------
+      // thread -> 4 items per chunk: rows (wt/8) + 32*i, granule (8 channels = 16 B of fp16) g = wt % 8
+      auto gather_pass = [&]() {
+        const int g = wt & 7;
+        int cur_scale = -1;
+        Taps taps[4];
+        for (int c = 0; c < kz; ++c) {
+          if (!((mask >> c) & 1ull)) continue;
+          const int ch = c * kChunkK + g * 8;                     // first of this thread's 8 channels
+          int s = -1;
+#pragma unroll
+          for (int i = 0; i < kScales; ++i)
+            if (ch >= p.ch_off[i] && ch < p.ch_off[i + 1]) s = i;
+          if (s >= 0 && s != cur_scale) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int2 sp = sph_smem[(wt >> 3) + 32 * i];
+              taps[i] = scale_taps(p, s, sp.x, sp.y);
+            }
+            cur_scale = s;
+          }
+          wait_slot();
+          const uint32_t slot_addr = smem_base + kSmemA + ra.slot * kASlotBytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = (wt >> 3) + 32 * i;
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+            if (s >= 0 && taps[i].any) {
+              const float* f = p.feat[s] + (ch - p.ch_off[s]);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                if (taps[i].off[t] >= 0) {
+                  const float4 v0 = __ldg(reinterpret_cast<const float4*>(f + taps[i].off[t]));
+                  const float4 v1 = __ldg(reinterpret_cast<const float4*>(f + taps[i].off[t]) + 1);
+                  const float w = taps[i].w[t];
+                  // out = ((v_nw*nw + v_ne*ne) + v_sw*sw) + v_se*se : separate roundings like ATen's CPU kernel
+                  acc[0] = fadd(acc[0], fmul(v0.x, w)); acc[1] = fadd(acc[1], fmul(v0.y, w));
+                  acc[2] = fadd(acc[2], fmul(v0.z, w)); acc[3] = fadd(acc[3], fmul(v0.w, w));
+                  acc[4] = fadd(acc[4], fmul(v1.x, w)); acc[5] = fadd(acc[5], fmul(v1.y, w));
+                  acc[6] = fadd(acc[6], fmul(v1.z, w)); acc[7] = fadd(acc[7], fmul(v1.w, w));
+                }
+              }
+            }
+            sts128(slot_addr + sw128_offset(row, g), pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
+                   pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]));
+          }
+          publish_chunk();
+        }
+      };
+
+      // ---------------- epilogue: ACC (TMEM) -> [+bias (+h)] -> (scratch) -> relu -> fp16 A chunks -------------
+      //   bias_idx: which header vector; use_h: add the fp32 hidden state from scratch; write_h: store it back
+      auto epilogue_to_act = [&](int bias_idx, bool use_h, bool write_h) {
+        mbar_wait(acc_full, acc_phase, a.error_flag);
+        acc_phase ^= 1;
+        tc_fence_after();
+        const float4* b4 = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden);
+        // this warp writes A slots of chunks [4*col_half, 4*col_half+4); slots of an epilogue are ra.slot+0..7
+        for (int grp = 0; grp < 8; ++grp) {
+          const int col = col_half * 256 + grp * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, v);
+          tmem_ld_wait();
+          const int chunk = col >> 6;
+          int slot = ra.slot + chunk;
+          uint32_t ph = ra.phase;
+          if (slot >= kASlots) { slot -= kASlots; ph ^= 1; }
+          if ((grp & 1) == 0) mbar_wait(a_empty(slot), ph ^ 1, a.error_flag);
+          const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {                        // 4 granules of 8 columns
+            float h[8];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int c4 = (col >> 2) + gq * 2 + half;          // float4 column index
+              const float4 bb = __ldg(b4 + c4);
+              float4 hh = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (use_h) hh = scratch4[(size_t)c4 * kTileM + erow];
+              float4 r;
+              r.x = __uint_as_float(v[gq * 8 + half * 4 + 0]) + bb.x + hh.x;
+              r.y = __uint_as_float(v[gq * 8 + half * 4 + 1]) + bb.y + hh.y;
+              r.z = __uint_as_float(v[gq * 8 + half * 4 + 2]) + bb.z + hh.z;
+              r.w = __uint_as_float(v[gq * 8 + half * 4 + 3]) + bb.w + hh.w;
+              if (write_h) scratch4[(size_t)c4 * kTileM + erow] = r;
+              h[half * 4 + 0] = fmaxf(r.x, 0.f); h[half * 4 + 1] = fmaxf(r.y, 0.f);
+              h[half * 4 + 2] = fmaxf(r.z, 0.f); h[half * 4 + 3] = fmaxf(r.w, 0.f);
+            }
+            const int gcol = ((col & 63) >> 3) + gq;              // granule inside the 64-wide chunk
+            sts128(slot_addr + sw128_offset(erow, gcol), pack_half2(h[0], h[1]), pack_half2(h[2], h[3]),
+                   pack_half2(h[4], h[5]), pack_half2(h[6], h[7]));
+          }
+        }
+        // every TMEM read and smem write of this warp is done: release all 8 chunks (the next MMA overwrites ACC)
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          for (int cidx = 0; cidx < kHiddenChunks; ++cidx) {
+            int slot = ra.slot + cidx;
+            if (slot >= kASlots) slot -= kASlots;
+            mbar_arrive(a_full(slot));
+          }
+        }
+        for (int cidx = 0; cidx < kHiddenChunks; ++cidx) ra.advance<kASlots>();
+      };
+
+      auto dump_acc = [&]() {                     // debug: raw accumulator of the current layer
+        mbar_wait(acc_full, acc_phase, a.error_flag);
+        acc_phase ^= 1;
+        tc_fence_after();
+        for (int grp = 0; grp < 8; ++grp) {
+          const int col = col_half * 256 + grp * 32;
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, v);
+          tmem_ld_wait();
+          float* dst = a.debug_acc + ((size_t)row0 + erow) * kHidden + col;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        named_bar_sync(1, kWorkerThreads);
+      };
+
+      // ---------------- the tile program ---------------------------------------------------------------------
+      bool stop = false;
+      auto after_layer = [&](int l) {              // debug hook: true -> this tile ends here
+        if (a.debug_layer == l) { dump_acc(); stop = true; }
+        return stop;
+      };
+      gather_pass();                                              // L1 lin_z0
+      if (after_layer(1)) continue;
+      for (int b = 0; b < SRF_NUM_BLOCKS && !stop; ++b) {
+        epilogue_to_act(/*bias*/ b, /*use_h*/ b > 0, /*write_h*/ true);        // E1 -> feeds fc_0
+        if (after_layer(2 + 3 * b)) break;
+        epilogue_to_act(/*bias*/ 3 + b, false, false);                          // E2 -> feeds fc_1
+        if (b < SRF_NUM_BLOCKS - 1) {
+          gather_pass();                                                        // lin_z(b+1)
+          if (after_layer(4 + 3 * b)) break;
+        } else {
+          if (after_layer(9)) break;
+        }
+      }
+      if (stop) continue;
+      epilogue_to_act(/*bias*/ 6, true, false);                                 // E3 -> feeds lin_out
+      if (after_layer(10)) continue;
+      // ---------------- E4: out = ACC[:, :d_out] + b_out ------------------------------------------------------
+      mbar_wait(acc_full, acc_phase, a.error_flag);
+      acc_phase ^= 1;
+      tc_fence_after();
+      if (col_half == 0) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16), v);   // 32 columns; only the first 16 are meaningful
+        tmem_ld_wait();
+        const int gi = row0 + erow;
+        if (gi < a.n) {
+          const float* bo = bias + (size_t)7 * kHidden;
+          for (int j = 0; j < a.d_out; ++j) a.raw_out[(size_t)gi * a.d_out + j] = __uint_as_float(v[j]) + __ldg(bo + j);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+    }
+  }
+
+  // ---- teardown -------------------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight packing: nn.Linear fp32 (out,in) -> header of epilogue bias vectors + fp16 stage images in consumption order
+// ---------------------------------------------------------------------------------------------------------------
+struct PackArgs {
+  srf_mlp_weights w;
+  int kz;
+};
+
+__device__ __forceinline__ const float* layer_weight(const srf_mlp_weights& w, int l, int& K) {
+  K = kHidden;
+  switch (l) {
+    case 0: K = kDX; return w.lin_in_w;
+    case 1: K = w.d_latent; return w.lin_z_w[0];
+    case 2: return w.fc0_w[0];
+    case 3: return w.fc1_w[0];
+    case 4: K = w.d_latent; return w.lin_z_w[1];
+    case 5: return w.fc0_w[1];
+    case 6: return w.fc1_w[1];
+    case 7: K = w.d_latent; return w.lin_z_w[2];
+    case 8: return w.fc0_w[2];
+    case 9: return w.fc1_w[2];
+    default: return w.lin_out_w;
+  }
+}
+
+// one thread per 16-byte granule of the image region
+__global__ void pack_images_kernel(const __grid_constant__ PackArgs pa, unsigned char* __restrict__ images, size_t n_granules) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_granules) return;
+  size_t byte = gid * 16;
+  // locate the layer
+  int l = 0;
+  size_t off = 0;
+  for (; l < kNumLayers; ++l) {
+    const size_t sz = (size_t)layer_chunks(l, pa.kz) * (kLayers[l].is_out ? kOutImgBytes : kQuarters * kBSlotBytes);
+    if (byte < off + sz) break;
+    off += sz;
+  }
+  const size_t rel = byte - off;
+  const bool is_out = kLayers[l].is_out;
+  const size_t chunk_bytes = is_out ? kOutImgBytes : (size_t)kQuarters * kBSlotBytes;
+  const int c = (int)(rel / chunk_bytes);
+  const size_t in_chunk = rel % chunk_bytes;
+  const int q = is_out ? 0 : (int)(in_chunk / kBSlotBytes);
+  const size_t in_img = is_out ? in_chunk : in_chunk % kBSlotBytes;
+  const int row = (int)(in_img / 128);
+  const int gpos = (int)((in_img % 128) / 16);
+  const int g = gpos ^ (row & 7);                      // logical granule stored at this swizzled position
+  const int n = q * kBRows + row;                      // output unit
+  int K;
+  const float* W = layer_weight(pa.w, l, K);
+  const int n_rows = is_out ? pa.w.d_out : kHidden;
+  __align__(16) __half hv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = c * kChunkK + g * 8 + j;
+    const float v = (n < n_rows && k < K) ? W[(size_t)n * K + k] : 0.0f;
+    hv[j] = __float2half_rn(v);
+  }
+  *reinterpret_cast<uint4*>(images + byte) = *reinterpret_cast<const uint4*>(hv);
+}
+
+__global__ void pack_header_kernel(const __grid_constant__ PackArgs pa, float* __restrict__ hdr) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= kHidden) return;
+  const srf_mlp_weights& w = pa.w;
+  // cumulative biases folded into the epilogues (see file header)
+  hdr[0 * kHidden + j] = w.lin_in_b[j] + w.lin_z_b[0][j];
+  hdr[1 * kHidden + j] = w.fc1_b[0][j] + w.lin_z_b[1][j];
+  hdr[2 * kHidden + j] = w.fc1_b[1][j] + w.lin_z_b[2][j];
+  hdr[3 * kHidden + j] = w.fc0_b[0][j];
+  hdr[4 * kHidden + j] = w.fc0_b[1][j];
+  hdr[5 * kHidden + j] = w.fc0_b[2][j];
+  hdr[6 * kHidden + j] = w.fc1_b[2][j];
+  hdr[7 * kHidden + j] = (j < w.d_out) ? w.lin_out_b[j] : 0.0f;
+}
+
+static size_t images_bytes(int kz) {
+  size_t b = 0;
+  const int chunks[kNumLayers] = {1, kz, 8, 8, kz, 8, 8, kz, 8, 8, 8};
+  for (int l = 0; l < kNumLayers; ++l) b += (size_t)chunks[l] * (l == kNumLayers - 1 ? kOutImgBytes : kQuarters * kBSlotBytes);
+  return b;
+}
+
+}  // namespace tc
+
+static inline int kz_of(int d_latent) { return (d_latent + tc::kChunkK - 1) / tc::kChunkK; }
+
+size_t tc_weights_bytes(int d_out, int d_latent) {
+  (void)d_out;
+  return tc::kHeaderBytes + tc::images_bytes(kz_of(d_latent)) + 256;
+}
+
+int pack_weights_tc(const srf_mlp_weights& w, void* dst, size_t bytes, cudaStream_t st) {
+  const int kz = kz_of(w.d_latent);
+  if (kz > 64 || w.d_out < 1 || w.d_out > tc::kOutN || (w.d_latent % 8)) return 1;
+  if (bytes < tc_weights_bytes(w.d_out, w.d_latent)) return 1;
+  tc::PackArgs pa;
+  pa.w = w;
+  pa.kz = kz;
+  tc::pack_header_kernel<<<(kHidden + 127) / 128, 128, 0, st>>>(pa, reinterpret_cast<float*>(dst));
+  const size_t n_gran = tc::images_bytes(kz) / 16;
+  tc::pack_images_kernel<<<(unsigned)((n_gran + 255) / 256), 256, 0, st>>>(
+      pa, reinterpret_cast<unsigned char*>(dst) + tc::kHeaderBytes, n_gran);
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+size_t tc_workspace_bytes(int d_latent, int n_points) {
+  (void)d_latent; (void)n_points;
+  return (size_t)256 * tc::kTileM * kHidden * sizeof(float) + 256;      // h scratch for up to 256 CTAs + error flag
+}
+
+int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n,
+                           int n_per, float* raw_out, int32_t* dbg_sphere, int flags, void* workspace, size_t ws_bytes,
+                           int debug_layer, float* debug_acc, cudaStream_t st) {
+  if (ws_bytes < tc_workspace_bytes(p.d_latent, n)) return -1;
+  if (debug_layer >= 0 && !(debug_layer < tc::kNumLayers && debug_layer != 0 && debug_layer != 3 && debug_layer != 6))
+    return -2;                         // layers without an ACC-complete signal cannot be dumped
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc::point_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
+    attr_set = true;
+  }
+  tc::KernelArgs a;
+  a.pts = pts; a.viewdir = viewdir; a.n = n; a.n_per = n_per;
+  a.n_tiles = (n + tc::kTileM - 1) / tc::kTileM;
+  a.kz = kz_of(p.d_latent);
+  a.wblob = reinterpret_cast<const unsigned char*>(w.tc_packed);
+  a.scratch = reinterpret_cast<float*>(workspace);
+  a.raw_out = raw_out; a.d_out = w.d_out; a.dbg_sphere = dbg_sphere;
+  a.skip_zero = (flags & SRF_FLAG_SKIP_ZERO_CHUNKS) ? 1 : 0;
+  a.debug_layer = debug_layer; a.debug_acc = debug_acc;
+  a.error_flag = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + (size_t)256 * tc::kTileM * kHidden * sizeof(float));
+  cudaMemsetAsync(a.error_flag, 0, sizeof(int), st);
+  int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
+  if (grid > 256) grid = 256;
+  tc::point_mlp_tc_kernel<<<grid, tc::kThreads, tc::kSmemTotal + 1024, st>>>(p, a);
+  return 2;
+}
+
+int run_point_mlp_tc(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n,
+                     int n_per, float* raw_out, int32_t* dbg_sphere, int flags, void* workspace, size_t ws_bytes,
+                     cudaStream_t st) {
+  return run_point_mlp_tc_debug(p, w, pts, viewdir, n, n_per, raw_out, dbg_sphere, flags, workspace, ws_bytes, -1,
+                                nullptr, st);
+}
+
 }  // namespace srf

@@ -273,6 +273,26 @@ class B200Renderer:
         res = raw.reshape(n_cols, n_per, d_out)
         return (res, dbg) if debug else res
 
+    def debug_tc_layer(self, mlp, cam_pts, x_rgb, cam_K, viewdir, layer: int):
+        """Diagnostic: raw fp32 TMEM accumulator (ceil(n/128)*128, 512) after `layer` of the tensor-core tile
+        program (include/scenerf_b200.h: srf_debug_tc_layer)."""
+        net = self._select(mlp)
+        if net.packed is None:
+            raise RuntimeError("renderer was not built with precision='fp16'")
+        pts = cam_pts.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        vd = viewdir.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        n_cols, n_per = pts.shape[0], pts.shape[1]
+        cfg = self._config(cam_K, None)
+        cfg.precision = _lib.PREC_FP16_TC
+        pyr = self._pack_pyramid(x_rgb)
+        n = n_cols * n_per
+        acc = torch.zeros(((n + 127) // 128 * 128, 512), dtype=torch.float32, device=self.device)
+        ws = self._workspace(self.lib.srf_predict_workspace_bytes(C.byref(cfg), n))
+        _lib.check(self.lib.srf_debug_tc_layer(C.byref(cfg), C.byref(pyr), C.byref(net.struct), _ptr(pts), _ptr(vd),
+                                               n_cols, n_per, int(layer), _ptr(acc), _ptr(ws), ws.numel(),
+                                               _stream_ptr(self.device)))
+        return acc
+
     def _select(self, mlp):
         if mlp in ("mlp", None) or mlp is self.mlp:
             return self.mlp
