@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- rays/sec of the SceneRF ray-render hot path on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload B|A|C] [--precision fp16|fp32]
+
+A "step" is one full render_rays_batch-equivalent pass (gaussian proposal MLP, sampling+sort, main MLP, compositing,
+RaySOM skipped as inference callers do, multi-GPU gather) over every ray of the workload:
+  workload B (default, BASELINE.json configs[1]): KITTI 1226x370 full-frame novel view, 453 620 rays x 128 samples.
+Features and weights are packed and resident before the timed region.  `value` times the device-resident
+call; `e2e` times the reference-facing host-buffer call (pinned pixels H2D + depth/rgb D2H inside the timed region).
+N > 1 (torchrun): frame-per-GPU layout -- every rank renders its own full frame (own pose) and the packed depth+rgb
+of all frames are all-gathered over NCCL; per-GPU work is fixed => "scaling": "weak".
+--impl reference times the CPU restatement of the reference (oracle/, pinned to the reference's own outputs) on the host
+cores with a process pool; the reference itself is PyTorch-on-Python and is not present on the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FLOP_MAIN = 2 * 5405696       # per main sample point  
+FLOP_GAUSS = 2 * 5404672      # per gaussian-proposal point
+
+
+def workload(name):
+    from scenerf_b200 import synth
+    if name == "A":
+        cfg = synth.config_A()
+        pix = synth.random_pixels(1, 1024, cfg.img_W, cfg.img_H)
+        desc = "A: KITTI single image, 1024 rays x 64 samples"
+    elif name == "C":
+        cfg = synth.config_C()
+        pix = synth.grid_pixels(cfg.img_W, cfg.img_H)
+        desc = "C: BundleFusion 640x480 full frame, 307200 rays x 96 samples"
+    else:
+        cfg = synth.config_B()
+        pix = synth.grid_pixels(cfg.img_W, cfg.img_H)
+        desc = "B: KITTI 1226x370 full-frame novel view, 453620 rays x 128 samples"
+    return cfg, np.ascontiguousarray(pix), desc
+
+
+def hp_from_cfg(cfg):
+    v_min, v_max, h_min, h_max = cfg.angles()
+    return dict(dataset=cfg.dataset, n_pts_uni=cfg.n_pts_uni, n_gaussians=cfg.n_gaussians,
+                n_pts_per_gaussian=cfg.n_pts_per_gaussian, std=cfg.std, max_sample_depth=cfg.max_sample_depth,
+                out_img_W=cfg.sphere_W, out_img_H=cfg.sphere_H, som_sigma=cfg.som_sigma, v_angle_min=v_min,
+                v_angle_max=v_max, h_angle_min=h_min, h_angle_max=h_max)
+
+
+def flop_per_ray(cfg):
+    return cfg.S * FLOP_MAIN + cfg.n_gaussians * FLOP_GAUSS
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(cfg, pyr_seed, blas_threads):
+    from threadpoolctl import threadpool_limits
+    from oracle.scenerf_oracle import OracleRenderer   # checker / CPU baseline only
+    from scenerf_b200 import synth
+    _CPU["limit"] = threadpool_limits(limits=blas_threads)
+    pm, pg = synth.make_model_params(cfg)
+    _CPU["r"] = OracleRenderer(cfg, pm, pg)
+    _CPU["cfg"] = cfg
+
+
+def _cpu_chunk(args):
+    pix, seed = args
+    cfg = _CPU["cfg"]
+    rng = np.random.default_rng(seed)
+    nu = rng.random((pix.shape[0], cfg.n_pts_uni), dtype=np.float32)
+    nn_ = rng.standard_normal((pix.shape[0], cfg.n_gaussians * cfg.n_pts_per_gaussian)).astype(np.float32)
+    out = _CPU["r"].render_rays_batch(cfg.K, cfg.T, _CPU["pyr"], pix, pix.shape[0], nu, nn_)
+    return float(out["depth"].sum())
+
+
+def cpu_rays_per_sec(cfg, pix, pyramid, target_seconds=15.0, chunk=128):
+    """Times the oracle on a bounded sample of the workload's rays with a fork pool over ray chunks."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    workers = max(1, min(32, cores // 2))
+    blas = max(1, cores // workers)
+    _CPU["pyr"] = pyramid                      # inherited by fork (copy-on-write, no pickling of 281 MB)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers, initializer=_cpu_init, initargs=(cfg, 0, blas)) as pool:
+        rng = np.random.default_rng(0)
+        sel = rng.permutation(pix.shape[0])
+        mk = lambda i: (np.ascontiguousarray(pix[sel[i * chunk:(i + 1) * chunk]]), i)
+        t0 = time.perf_counter()
+        pool.map(_cpu_chunk, [mk(i) for i in range(workers)])            # warm-up + calibration round
+        t_round = time.perf_counter() - t0
+        rounds = int(max(1, min(20, target_seconds / max(t_round, 1e-3))))
+        n_chunks = workers * rounds
+        t0 = time.perf_counter()
+        pool.map(_cpu_chunk, [mk(workers + i) for i in range(n_chunks)])
+        dt = time.perf_counter() - t0
+    n_rays = n_chunks * chunk
+    return n_rays / dt, dict(cores=workers * blas, workers=workers, blas_threads=blas,
+                             sample="%d rays x %d samples of the workload (random subset, %d-ray chunks), %.1f s"
+                                    % (n_rays, cfg.S, chunk, dt))
+
+
+def make_cpu_pyramid(cfg, seed=5):
+    rng = np.random.default_rng(seed)
+    from scenerf_b200 import synth
+    return {k: (rng.standard_normal((c, h, w), dtype=np.float32) * np.float32(0.5))
+            for k, (c, h, w) in zip(synth.SCALE_KEYS, synth.pyramid_shapes(cfg.sphere_W, cfg.sphere_H))}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cfg, pix, desc = workload(args.workload)
+    pyr = make_cpu_pyramid(cfg)
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        v, info = cpu_rays_per_sec(cfg, pix, pyr, target_seconds=8.0)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {"metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": desc, "what": "CPU restatement of the reference (oracle/, numpy+OpenBLAS) on host cores"},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": info["cores"], "kind": "port",
+                             "sample": info["sample"]},
+            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="B", choices=["A", "B", "C"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--skip-zero-chunks", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from scenerf_b200 import synth
+    from scenerf_b200 import dist as sdist
+    from scenerf_b200.renderer import B200Renderer
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, pix_np, desc = workload(args.workload)
+    cfg.tz = cfg.tz + 0.5 * rank                      # frame-per-GPU: every rank renders its own pose
+    R = pix_np.shape[0]
+    pm, pg = synth.make_model_params(cfg)
+    to_t = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    r = B200Renderer(hp_from_cfg(cfg), to_t(pm), to_t(pg), device=dev, precision=args.precision, rng="philox",
+                     skip_zero_chunks=bool(args.skip_zero_chunks))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5 + rank)
+    x_rgb = {k: torch.randn((c, h, w), generator=gen, device=dev) * 0.5
+             for k, (c, h, w) in zip(synth.SCALE_KEYS, synth.pyramid_shapes(cfg.sphere_W, cfg.sphere_H))}
+    K, T = torch.from_numpy(cfg.K), torch.from_numpy(cfg.T)
+    pix_host = torch.from_numpy(pix_np).pin_memory()
+    pix_dev = pix_host.to(dev)
+    r.set_profiling(True)
+
+    def step_device():
+        out = r.render_rays_batch(K, T, x_rgb, sampled_pixels=pix_dev, outputs="minimal")
+        if world > 1:
+            return sdist.gather_frames(out["depth"], out["color"])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mlp_ms = []
+    launches = 0
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+        launches += r.last_launches
+        mlp_ms.append(r.last_mlp_ms()[1])            # waits for this step's main-MLP end event only
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    value = world * R / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, through the reference-facing call ------------------------------
+    out_host = {"depth": torch.empty((R,), dtype=torch.float32).pin_memory(),
+                "color": torch.empty((R, 3), dtype=torch.float32).pin_memory()}
+    r.render_rays_batch_host(K, T, x_rgb, pix_host, out_host)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        r.render_rays_batch_host(K, T, x_rgb, pix_host, out_host)
+        if world > 1:
+            sdist.gather_frames(out_host["depth"].to(dev, non_blocking=True), out_host["color"].to(dev, non_blocking=True))
+    e1.record()
+    barrier()
+    ems = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_value = world * R / (float(ems.item()) / args.steps * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (main point-MLP pass), measured live with CUDA events ------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (fp16 and bf16 share the tcgen05 kind::f16 rate)" \
+        if peaks else "fallback 1.4 PF sustained (B200_PROFILING.md)"
+    main_ms = float(np.mean([m for m in mlp_ms if m > 0])) if mlp_ms else float("nan")
+    flop_launch = float(R) * cfg.S * FLOP_MAIN
+    achieved = flop_launch / (main_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload + "_" + args.precision)
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "point_mlp_tc_kernel (main pass)" if args.precision == "fp16" else "sgemm_nt_kernel chain",
+                "kernel_ms": main_ms, "algorithmic_flop_per_launch": flop_launch, "peak_source": peak_src,
+                "whole_step_tflops": world * R * flop_per_ray(cfg) / (ms_per_step * 1e-3) / 1e12}
+
+    cpu = None
+    parity = None
+    if not args.no_cpu_baseline:
+        pyr_cpu = {k: v.detach().cpu().numpy() for k, v in x_rgb.items()}
+        v, info = cpu_rays_per_sec(cfg, pix_np, pyr_cpu, target_seconds=15.0)
+        cpu = {"value": v, "unit": "rays/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
+        # parity of this very run: same rays, weights, pyramid and noise through the oracle and through the GPU path
+        from oracle.scenerf_oracle import OracleRenderer
+        n = 64
+        rng = np.random.default_rng(1)
+        sel = rng.permutation(R)[:n]
+        nu = rng.random((n, cfg.n_pts_uni), dtype=np.float32)
+        nn_ = rng.standard_normal((n, cfg.n_gaussians * cfg.n_pts_per_gaussian)).astype(np.float32)
+        ref = OracleRenderer(cfg, pm, pg).render_rays_batch(cfg.K, cfg.T, pyr_cpu, pix_np[sel], n, nu, nn_)
+        got = r.render_rays_batch(K, T, x_rgb, sampled_pixels=torch.from_numpy(pix_np[sel]), outputs="minimal",
+                                  noise=(torch.from_numpy(nu), torch.from_numpy(nn_)))
+        parity = {"rays": n, "depth_max_abs_err_m": float(np.abs(got["depth"].cpu().numpy() - ref["depth"]).max()),
+                  "color_max_abs_err": float(np.abs(got["color"].cpu().numpy() - ref["color"]).max()),
+                  "vs": "CPU oracle (pinned to the reference), identical rays/weights/noise"}
+
+    line = {"metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp16" if args.precision == "fp16" else "f32", "data": "synthetic",
+            "config": {"workload": desc, "rays_per_gpu": R, "samples_per_ray": cfg.S, "parallelism": "frame-per-GPU x%d" % world,
+                       "precision": args.precision + (" operands, fp32 accumulate (tcgen05)" if args.precision == "fp16" else " SIMT"),
+                       "skip_zero_chunks": bool(args.skip_zero_chunks), "outputs": "depth+color",
+                       "l2": "inputs larger than L2: 281 MB pyramid + 0.9 GB of per-step intermediates; no flush needed"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": R * 2 * 4, "d2h_bytes_per_step": R * 4 * 4},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

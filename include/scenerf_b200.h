@@ -167,6 +167,12 @@ int srf_debug_tc_layer(const srf_config* cfg, const srf_pyramid* pyr, const srf_
                        const float* cam_pts_dev, const float* viewdir_dev, int n_cols, int n_per, int layer,
                        float* acc_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Device-side timing of the point-MLP passes of the calls that follow on this thread (CUDA events recorded on the
+ * call's stream around the mlp_gaussian pass and the main mlp pass).  srf_last_mlp_ms waits for the end events of
+ * the most recent call and returns the elapsed milliseconds (-1 if that pass did not run). */
+void srf_set_profiling(int on);
+int srf_last_mlp_ms(float* gauss_ms, float* main_ms);
+
 /* Number of kernels the last srf_render_rays / srf_predict call on this thread launched (bench "gpu_launches"). */
 int srf_last_launch_count(void);
 

@@ -133,13 +133,28 @@ size_t mlp_workspace_bytes(int precision, int d_latent, int n_points) {
                                     : srf::tc_workspace_bytes(d_latent, n_points);
 }
 
+// optional device-side timing of the two point-MLP passes (bench.py roofline): events on the launching stream
+thread_local bool g_profiling = false;
+thread_local cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // gauss begin/end, main begin/end
+thread_local bool g_ev_valid[2] = {false, false};
+
+void prof_record(int which, cudaStream_t st) {
+  if (!g_profiling) return;
+  if (!g_ev[which]) cudaEventCreate(&g_ev[which]);
+  cudaEventRecord(g_ev[which], st);
+  if (which & 1) g_ev_valid[which >> 1] = true;
+}
+
 int run_mlp(const srf::DevParams& p, int precision, int flags, const srf_mlp_weights& w, const float* pts,
             const float* viewdir, int n, int n_per, float* raw, int32_t* dbg, void* ws, size_t ws_bytes,
             cudaStream_t st) {
   int l;
+  const int pass = (w.d_out == 4) ? 1 : 0;
+  prof_record(2 * pass, st);
   if (precision == SRF_PREC_FP32) l = srf::run_point_mlp_simt(p, w, pts, viewdir, n, n_per, raw, dbg, ws, ws_bytes, st);
   else l = srf::run_point_mlp_tc(p, w, pts, viewdir, n, n_per, raw, dbg, flags, ws, ws_bytes, st);
   if (l < 0) return fail(SRF_E_WORKSPACE, "point-MLP workspace too small (%zu bytes)", ws_bytes);
+  prof_record(2 * pass + 1, st);
   g_launches += l;
   return check_cuda("point MLP");
 }
@@ -187,6 +202,18 @@ extern "C" {
 int srf_abi_version(void) { return SRF_ABI_VERSION; }
 const char* srf_last_error(void) { return g_err; }
 int srf_last_launch_count(void) { return g_launches; }
+void srf_set_profiling(int on) { g_profiling = on != 0; }
+int srf_last_mlp_ms(float* gauss_ms, float* main_ms) {
+  float* dst[2] = {gauss_ms, main_ms};
+  for (int i = 0; i < 2; ++i) {
+    if (!dst[i]) continue;
+    *dst[i] = -1.0f;
+    if (!g_ev_valid[i]) continue;
+    if (cudaEventSynchronize(g_ev[2 * i + 1]) != cudaSuccess) return check_cuda("srf_last_mlp_ms");
+    cudaEventElapsedTime(dst[i], g_ev[2 * i], g_ev[2 * i + 1]);
+  }
+  return SRF_OK;
+}
 size_t srf_sizeof(int which) {
   switch (which) {
     case 0: return sizeof(srf_config);

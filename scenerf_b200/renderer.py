@@ -273,6 +273,40 @@ class B200Renderer:
         res = raw.reshape(n_cols, n_per, d_out)
         return (res, dbg) if debug else res
 
+    def render_rays_batch_host(self, cam_K, T_source2infer, x_rgb, sampled_pixels_host, out_host=None):
+        """Same call with HOST buffers (include/scenerf_b200.h: srf_render_rays_host): `sampled_pixels_host` is a CPU
+        tensor (pinned for full-speed copies); the rays go host->device, are rendered, and depth (R) + color (R,3)
+        come back into CPU tensors, all on the current stream, which is synchronised on return."""
+        pix = sampled_pixels_host
+        if pix.device.type != "cpu" or pix.dtype != torch.float32 or not pix.is_contiguous():
+            raise ValueError("sampled_pixels_host must be a contiguous float32 CPU tensor")
+        R = int(pix.shape[0])
+        cfg = self._config(cam_K, T_source2infer)
+        pyr = self._pack_pyramid(x_rgb)
+        if out_host is None:
+            out_host = {"depth": torch.empty((R,), dtype=torch.float32).pin_memory(),
+                        "color": torch.empty((R, 3), dtype=torch.float32).pin_memory()}
+        out = Outputs()
+        out.depth, out.color = out_host["depth"].data_ptr(), out_host["color"].data_ptr()
+        self.seed += 1
+        cfg.seed = self.seed
+        nbytes = self.lib.srf_render_host_workspace_bytes(C.byref(cfg), R)
+        ws = self._workspace(nbytes)
+        _lib.check(self.lib.srf_render_rays_host(C.byref(cfg), C.byref(pyr), C.byref(self.mlp.struct),
+                                                 C.byref(self.mlp_gaussian.struct), C.c_void_p(pix.data_ptr()), R,
+                                                 C.byref(out), _ptr(ws), ws.numel(), _stream_ptr(self.device)))
+        self.last_launches = self.lib.srf_last_launch_count()
+        return out_host
+
+    def set_profiling(self, on: bool):
+        self.lib.srf_set_profiling(1 if on else 0)
+
+    def last_mlp_ms(self):
+        """(mlp_gaussian pass ms, main mlp pass ms) of the most recent render call, from CUDA events."""
+        g, m = C.c_float(-1.0), C.c_float(-1.0)
+        _lib.check(self.lib.srf_last_mlp_ms(C.byref(g), C.byref(m)))
+        return g.value, m.value
+
     def debug_tc_layer(self, mlp, cam_pts, x_rgb, cam_K, viewdir, layer: int):
         """Diagnostic: raw fp32 TMEM accumulator (ceil(n/128)*128, 512) after `layer` of the tensor-core tile
         program (include/scenerf_b200.h: srf_debug_tc_layer)."""
