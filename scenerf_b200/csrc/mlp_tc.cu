@@ -23,6 +23,7 @@
 // Warp roles (320 threads, 1 CTA / SM):  warp 0 = weight producer (bulk copies), warp 1 = MMA issuer + TMEM owner,
 // warps 2..9 = 256 workers: geometry front-end, A-chunk producers (gather / activations) and TMEM epilogues.
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "kernels.cuh"
 
 namespace srf {
@@ -127,6 +128,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+// one slice of a weight image -> the same shared-memory offset of every CTA in `mask`, each CTA's own mbarrier
+// (same offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -146,6 +160,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// same, but the arrive is delivered to the barrier at this offset in every CTA of `mask` (cluster-shared weight ring)
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -241,9 +261,12 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
   volatile unsigned long long* mask_smem = reinterpret_cast<volatile unsigned long long*>(smem + kSmemMask);
   int2* sph_smem = reinterpret_cast<int2*>(smem + kSmemSph);
 
+  const uint32_t cs = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kASlots; ++s) { mbar_init(a_full(s), kWorkerWarps); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < kBSlots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    // a weight slot is free again only when the MMAs of every CTA sharing the multicast stream have consumed it
+    for (int s = 0; s < kBSlots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), cs); }
     mbar_init(acc_full, 1);
     mbar_init(meta_full, kWorkerWarps);
     fence_barrier_init();
@@ -251,8 +274,14 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
   if (warp == 1) tmem_alloc(smem_base + kSmemTmemPtr, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();            // peers must not multicast into / arrive on uninitialised barriers
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // tiles: cluster g handles tile groups g, g+n_clusters, ...; CTA `crank` takes tile group*cs + crank.  All CTAs of a
+  // cluster run the same number of tiles (a tile index >= n_tiles is a dummy with no valid rows) because they
+  // consume one shared weight stream in lock-step.
+  const int n_clusters = gridDim.x / cs, cluster_id = blockIdx.x / cs;
+  const int n_groups = (a.n_tiles + cs - 1) / cs;
 
   const int kz = a.kz;
   const int last_layer = (a.debug_layer >= 0) ? a.debug_layer : (kNumLayers - 1);
@@ -263,7 +292,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     if (lane == 0) {
       Ring rb;
       uint32_t meta_phase = 0;
-      for (int tile = blockIdx.x, it = 0; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      for (int grp_i = cluster_id, it = 0; grp_i < n_groups; grp_i += n_clusters, ++it) {
         uint64_t mask = ~0ull;
         bool have_mask = !a.skip_zero;
         size_t off = 0;
@@ -282,7 +311,13 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
               for (int q = 0; q < nimg; ++q) {
                 mbar_wait(b_empty(rb.slot), rb.phase ^ 1, a.error_flag);
                 mbar_arrive_expect_tx(b_full(rb.slot), bytes);
-                bulk_g2s(smem_base + kSmemB + rb.slot * kBSlotBytes, images + off + (size_t)q * bytes, bytes, b_full(rb.slot));
+                if (cs == 1) {
+                  bulk_g2s(smem_base + kSmemB + rb.slot * kBSlotBytes, images + off + (size_t)q * bytes, bytes, b_full(rb.slot));
+                } else {
+                  const uint32_t part = bytes / cs;      // this CTA fetches 1/cs of the image for the whole cluster
+                  bulk_g2s_multicast(smem_base + kSmemB + rb.slot * kBSlotBytes + crank * part,
+                                     images + off + (size_t)q * bytes + (size_t)crank * part, part, b_full(rb.slot), cmask);
+                }
                 rb.advance<kBSlots>();
               }
             }
@@ -299,7 +334,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       uint32_t meta_phase = 0;
       const uint32_t idesc_main = make_idesc(kTileM, kBRows);
       const uint32_t idesc_out = make_idesc(kTileM, kOutN);
-      for (int tile = blockIdx.x, it = 0; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      for (int grp_i = cluster_id, it = 0; grp_i < n_groups; grp_i += n_clusters, ++it) {
         uint64_t mask = ~0ull;
         bool have_mask = !a.skip_zero;
         for (int l = 0; l <= last_layer; ++l) {
@@ -327,7 +362,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
                 umma_f16(tmem_base + (uint32_t)(q * kBRows), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
                          is_out ? idesc_out : idesc_main, (first && k == 0) ? 0u : 1u);
               }
-              umma_commit(b_empty(rb.slot));
+              if (cs == 1) umma_commit(b_empty(rb.slot));
+              else umma_commit_multicast(b_empty(rb.slot), cmask);
               rb.advance<kBSlots>();
             }
             first = false;
@@ -359,7 +395,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     };
     auto wait_slot = [&]() { mbar_wait(a_empty(ra.slot), ra.phase ^ 1, a.error_flag); };
 
-    for (int tile = blockIdx.x, it = 0; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    for (int grp_i = cluster_id, it = 0; grp_i < n_groups; grp_i += n_clusters, ++it) {
+      const int tile = grp_i * (int)cs + (int)crank;
       const int row0 = tile * kTileM;
       // ---------------- front-end: geometry of this tile's 128 points (threads 0..127, one point each) --------
       float px = 0.f, py = 0.f, pz = 0.f;
@@ -531,8 +568,10 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, v);
           tmem_ld_wait();
           float* dst = a.debug_acc + ((size_t)row0 + erow) * kHidden + col;
+          if (tile < a.n_tiles) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(v[j]);
+          }
         }
         tc_fence_before();
         named_bar_sync(1, kWorkerThreads);
@@ -582,6 +621,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
   // ---- teardown -------------------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();            // no CTA may exit while a peer can still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -706,6 +746,16 @@ static int num_sms() {
   return g_num_sms;
 }
 
+static int tc_cluster_size() {
+  static int cs = -1;
+  if (cs < 0) {
+    const char* e = getenv("SRF_TC_CLUSTER");
+    cs = e ? atoi(e) : 2;
+    if (cs != 1 && cs != 2 && cs != 4 && cs != 8) cs = 1;
+  }
+  return cs;
+}
+
 size_t tc_workspace_bytes(int d_latent, int n_points) {
   (void)d_latent; (void)n_points;
   return (size_t)256 * tc::kTileM * kHidden * sizeof(float) + 256;      // h scratch for up to 256 CTAs + error flag
@@ -733,9 +783,34 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
   a.debug_layer = debug_layer; a.debug_acc = debug_acc;
   a.error_flag = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + (size_t)256 * tc::kTileM * kHidden * sizeof(float));
   cudaMemsetAsync(a.error_flag, 0, sizeof(int), st);
-  int grid = a.n_tiles < num_sms() ? a.n_tiles : num_sms();
-  if (grid > 256) grid = 256;
-  tc::point_mlp_tc_kernel<<<grid, tc::kThreads, tc::kSmemTotal + 1024, st>>>(p, a);
+  // Cluster size of the shared weight stream (1 = private stream per CTA).  Skipping zero chunks needs a per-tile
+  // chunk mask, which is CTA-private for now -> private streams in that mode.
+  int cs = tc_cluster_size();
+  if (a.skip_zero || a.n_tiles < 2 * cs) cs = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = tc::kSmemTotal + 1024;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int max_ctas = num_sms();
+  if (cs > 1) {
+    static int max_clusters[9] = {0};
+    if (!max_clusters[cs]) {
+      cfg.gridDim = dim3(num_sms() / cs * cs);
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, tc::point_mlp_tc_kernel, &cfg) != cudaSuccess || nc < 1) nc = num_sms() / cs / 2;
+      max_clusters[cs] = nc;
+    }
+    max_ctas = max_clusters[cs] * cs;
+  }
+  const int n_groups = (a.n_tiles + cs - 1) / cs;
+  int grid = n_groups * cs < max_ctas ? n_groups * cs : max_ctas;
+  if (grid > 256) grid = 256 / cs * cs;
+  cfg.gridDim = dim3(grid);
+  cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel, p, a);
   return 2;
 }
 
