@@ -22,6 +22,13 @@
 //
 // Warp roles (320 threads, 1 CTA / SM):  warp 0 = weight producer (bulk copies), warp 1 = MMA issuer + TMEM owner,
 // warps 2..9 = 256 workers: geometry front-end, A-chunk producers (gather / activations) and TMEM epilogues.
+//
+// CTA pairs (template CG = 2, the default): two CTAs of a 2-cluster run `tcgen05.mma.cta_group::2` with M = 256 --
+// each CTA owns a 128-point tile (its own A tiles, its own 128 TMEM lanes) but stages only HALF of every weight tile
+// (N = 256 per MMA, 128 rows per CTA), which halves the bytes every SM has to pull from L2 per FLOP.  Only the
+// leader CTA (rank 0) issues MMAs; the peer's workers arrive remotely on the leader's A-full barriers, the peer's
+// warp 1 relays its weight-full barriers to the leader, and the leader's tcgen05.commit multicasts the "empty" /
+// "accumulator complete" signals to both CTAs.  CG = 1 is the single-CTA variant (M = 128, N = 128).
 #include <cuda_fp16.h>
 #include <cstdlib>
 #include "kernels.cuh"
@@ -128,44 +135,89 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
-// one slice of a weight image -> the same shared-memory offset of every CTA in `mask`, each CTA's own mbarrier
-// (same offset) receives the complete_tx
-__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-               : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+// shared::cluster address of `local_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
 }
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T ; kind::f16, single-CTA
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void atom_or_remote_u64(uint32_t cluster_addr, unsigned long long v) {
+  asm volatile("red.relaxed.cluster.shared::cluster.or.b64 [%0], %1;" ::"r"(cluster_addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
       : "memory");
+  return ok != 0;
 }
-// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+// wait on a barrier that CTAs of the cluster arrive on remotely (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* error_flag) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) mbar_timeout(error_flag, bar, parity);
+  }
+}
+
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; kind::f16.  CG=2: issued by the leader CTA for the pair (M=256, each CTA
+// contributes its own A tile and half of the B rows, found at the same shared-memory offsets in both CTAs).
+template <int CG>
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed; CG=2: the arrive is
+// delivered to the barrier at this offset in BOTH CTAs of the pair
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// same, but the arrive is delivered to the barrier at this offset in every CTA of `mask` (cluster-shared weight ring)
-__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask)
-               : "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask)
+                 : "memory");
+  }
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -243,6 +295,7 @@ __device__ __forceinline__ uint64_t chunk_mask_for_scales(const DevParams& p, ui
 // ---------------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------------
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__ KernelArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -261,38 +314,42 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
   volatile unsigned long long* mask_smem = reinterpret_cast<volatile unsigned long long*>(smem + kSmemMask);
   int2* sph_smem = reinterpret_cast<int2*>(smem + kSmemSph);
 
-  const uint32_t cs = cluster_nctarank(), crank = cluster_ctarank();
-  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+  const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader of the pair
+  const bool leader = (crank == 0);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kASlots; ++s) { mbar_init(a_full(s), kWorkerWarps); mbar_init(a_empty(s), 1); }
-    // a weight slot is free again only when the MMAs of every CTA sharing the multicast stream have consumed it
-    for (int s = 0; s < kBSlots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), cs); }
+    // A-full: every worker warp of every CTA of the group arrives (on the leader's barrier)
+    for (int s = 0; s < kASlots; ++s) { mbar_init(a_full(s), kWorkerWarps * CG); mbar_init(a_empty(s), 1); }
+    // B-full: the local producer's arrive.expect_tx (+ its bytes); on the leader of a pair also the peer's relay
+    for (int s = 0; s < kBSlots; ++s) { mbar_init(b_full(s), (CG == 2 && leader) ? 2 : 1); mbar_init(b_empty(s), 1); }
     mbar_init(acc_full, 1);
-    mbar_init(meta_full, kWorkerWarps);
+    mbar_init(meta_full, kWorkerWarps * CG);
+    mask_smem[0] = 0ull; mask_smem[1] = 0ull;
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_base + kSmemTmemPtr, kTmemCols);
+  if (warp == 1) tmem_alloc<CG>(smem_base + kSmemTmemPtr, kTmemCols);
   tc_fence_before();
   __syncthreads();
-  if (cs > 1) cluster_sync_all();            // peers must not multicast into / arrive on uninitialised barriers
+  if (CG == 2) cluster_sync_all();           // the peer must not arrive on uninitialised barriers
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // tiles: cluster g handles tile groups g, g+n_clusters, ...; CTA `crank` takes tile group*cs + crank.  All CTAs of a
-  // cluster run the same number of tiles (a tile index >= n_tiles is a dummy with no valid rows) because they
-  // consume one shared weight stream in lock-step.
-  const int n_clusters = gridDim.x / cs, cluster_id = blockIdx.x / cs;
-  const int n_groups = (a.n_tiles + cs - 1) / cs;
+  // tiles: CTA group g handles tile groups g, g+n_cgroups, ...; CTA `crank` takes tile group*CG + crank.  Both CTAs
+  // of a pair run the same number of tiles (a tile index >= n_tiles is a dummy with no valid rows).
+  const int n_cgroups = gridDim.x / CG, cgroup_id = blockIdx.x / CG;
+  const int n_groups = (a.n_tiles + CG - 1) / CG;
 
   const int kz = a.kz;
   const int last_layer = (a.debug_layer >= 0) ? a.debug_layer : (kNumLayers - 1);
   const unsigned char* images = a.wblob + kHeaderBytes;
+  constexpr int kImgPerChunk = kQuarters / CG;          // weight images this CTA stages per A chunk
+  constexpr int kMmaN = kBRows * CG;                    // N of one MMA (128 rows from each CTA of the group)
 
   if (warp == 0) {
     // ===================================== weight producer =====================================================
+    // CG=2: CTA r stages rows [128 r, 128 r + 128) of every N=256 half, i.e. blob quarter q = 2*half + r.
     if (lane == 0) {
       Ring rb;
       uint32_t meta_phase = 0;
-      for (int grp_i = cluster_id, it = 0; grp_i < n_groups; grp_i += n_clusters, ++it) {
+      for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
         uint64_t mask = ~0ull;
         bool have_mask = !a.skip_zero;
         size_t off = 0;
@@ -300,77 +357,100 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           const int nc = layer_chunks(l, kz);
           const bool is_out = kLayers[l].is_out;
           if (kLayers[l].chunks_is_kz && !have_mask) {
-            mbar_wait(meta_full, meta_phase, a.error_flag);        // workers published this tile's chunk mask
+            mbar_wait_cluster(meta_full, meta_phase, a.error_flag);     // this tile group's chunk mask is published
             mask = mask_smem[it & 1];
             have_mask = true;
           }
           for (int c = 0; c < nc; ++c) {
-            const int nimg = is_out ? 1 : kQuarters;
-            const uint32_t bytes = is_out ? kOutImgBytes : kBSlotBytes;
+            const size_t chunk_bytes = is_out ? (size_t)kOutImgBytes : (size_t)kQuarters * kBSlotBytes;
             if (chunk_active(l, c, mask)) {
-              for (int q = 0; q < nimg; ++q) {
+              const int nimg = is_out ? 1 : kImgPerChunk;
+              const uint32_t bytes = is_out ? kOutImgBytes / CG : kBSlotBytes;
+              for (int i = 0; i < nimg; ++i) {
+                const size_t src = is_out ? (size_t)crank * bytes : (size_t)(i * CG + crank) * kBSlotBytes;
                 mbar_wait(b_empty(rb.slot), rb.phase ^ 1, a.error_flag);
                 mbar_arrive_expect_tx(b_full(rb.slot), bytes);
-                if (cs == 1) {
-                  bulk_g2s(smem_base + kSmemB + rb.slot * kBSlotBytes, images + off + (size_t)q * bytes, bytes, b_full(rb.slot));
-                } else {
-                  const uint32_t part = bytes / cs;      // this CTA fetches 1/cs of the image for the whole cluster
-                  bulk_g2s_multicast(smem_base + kSmemB + rb.slot * kBSlotBytes + crank * part,
-                                     images + off + (size_t)q * bytes + (size_t)crank * part, part, b_full(rb.slot), cmask);
-                }
+                bulk_g2s(smem_base + kSmemB + rb.slot * kBSlotBytes, images + off + src, bytes, b_full(rb.slot));
                 rb.advance<kBSlots>();
               }
             }
-            off += (size_t)nimg * bytes;
+            off += chunk_bytes;
           }
         }
         if (a.skip_zero) meta_phase ^= 1;
       }
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer ==========================================================
-    if (lane == 0) {
+    if (lane == 0 && leader) {
+      // ===================================== MMA issuer (leader CTA) ===========================================
       Ring ra, rb;
       uint32_t meta_phase = 0;
-      const uint32_t idesc_main = make_idesc(kTileM, kBRows);
-      const uint32_t idesc_out = make_idesc(kTileM, kOutN);
-      for (int grp_i = cluster_id, it = 0; grp_i < n_groups; grp_i += n_clusters, ++it) {
+      const uint32_t idesc_main = make_idesc(kTileM * CG, kMmaN);
+      const uint32_t idesc_out = make_idesc(kTileM * CG, kOutN);
+      for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
         uint64_t mask = ~0ull;
         bool have_mask = !a.skip_zero;
         for (int l = 0; l <= last_layer; ++l) {
           const int nc = layer_chunks(l, kz);
           const bool is_out = kLayers[l].is_out;
           if (kLayers[l].chunks_is_kz && !have_mask) {
-            mbar_wait(meta_full, meta_phase, a.error_flag);
+            mbar_wait_cluster(meta_full, meta_phase, a.error_flag);
             mask = mask_smem[it & 1];
             have_mask = true;
           }
           bool first = kLayers[l].fresh;           // the first executed chunk of a fresh layer overwrites ACC
           for (int c = 0; c < nc; ++c) {
             if (!chunk_active(l, c, mask)) continue;
-            mbar_wait(a_full(ra.slot), ra.phase, a.error_flag);
+            mbar_wait_cluster(a_full(ra.slot), ra.phase, a.error_flag);
             tc_fence_after();
             const uint64_t adesc = make_desc_sw128(smem_base + kSmemA + ra.slot * kASlotBytes);
-            const int nq = is_out ? 1 : kQuarters;
-            for (int q = 0; q < nq; ++q) {
-              mbar_wait(b_full(rb.slot), rb.phase, a.error_flag);
+            const int nh = is_out ? 1 : kImgPerChunk;
+            for (int h = 0; h < nh; ++h) {
+              mbar_wait_cluster(b_full(rb.slot), rb.phase, a.error_flag);
               tc_fence_after();
               const uint64_t bdesc = make_desc_sw128(smem_base + kSmemB + rb.slot * kBSlotBytes);
 #pragma unroll
               for (int k = 0; k < kChunkK / 16; ++k) {
                 // +32 bytes per UMMA_K=16 fp16 inside the swizzle atom row: start address field += 2
-                umma_f16(tmem_base + (uint32_t)(q * kBRows), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
-                         is_out ? idesc_out : idesc_main, (first && k == 0) ? 0u : 1u);
+                umma_f16<CG>(tmem_base + (uint32_t)(h * kMmaN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                             is_out ? idesc_out : idesc_main, (first && k == 0) ? 0u : 1u);
               }
-              if (cs == 1) umma_commit(b_empty(rb.slot));
-              else umma_commit_multicast(b_empty(rb.slot), cmask);
+              umma_commit<CG>(b_empty(rb.slot));
               rb.advance<kBSlots>();
             }
             first = false;
-            umma_commit(a_empty(ra.slot));
+            umma_commit<CG>(a_empty(ra.slot));
             ra.advance<kASlots>();
           }
-          if (kLayers[l].signal || l == last_layer) umma_commit(acc_full);
+          if (kLayers[l].signal || l == last_layer) umma_commit<CG>(acc_full);
+        }
+        if (a.skip_zero) meta_phase ^= 1;
+      }
+    } else if (CG == 2 && lane == 0 && !leader) {
+      // ===================================== weight-full relay (peer CTA) ======================================
+      // walks the same image sequence as the producer; when a local image has landed, arrives on the leader's
+      // barrier of the same slot (the leader's MMA reads this CTA's half of B through the pair datapath)
+      Ring rb;
+      uint32_t meta_phase = 0;
+      for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
+        uint64_t mask = ~0ull;
+        bool have_mask = !a.skip_zero;
+        for (int l = 0; l <= last_layer; ++l) {
+          const int nc = layer_chunks(l, kz);
+          if (kLayers[l].chunks_is_kz && !have_mask) {
+            mbar_wait_cluster(meta_full, meta_phase, a.error_flag);
+            mask = mask_smem[it & 1];
+            have_mask = true;
+          }
+          for (int c = 0; c < nc; ++c) {
+            if (!chunk_active(l, c, mask)) continue;
+            const int nimg = kLayers[l].is_out ? 1 : kImgPerChunk;
+            for (int i = 0; i < nimg; ++i) {
+              mbar_wait(b_full(rb.slot), rb.phase, a.error_flag);
+              mbar_arrive_remote(map_to_cta(b_full(rb.slot), 0));
+              rb.advance<kBSlots>();
+            }
+          }
         }
         if (a.skip_zero) meta_phase ^= 1;
       }
@@ -387,16 +467,22 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     uint32_t acc_phase = 0;
 
     // -- helpers -------------------------------------------------------------------------------------------
+    // A-full barriers live in the leader CTA: the MMA issuer there consumes the A tiles of both CTAs of a pair
+    auto arrive_a_full = [&](int slot) {
+      if constexpr (CG == 1) mbar_arrive(a_full(slot));
+      else mbar_arrive_remote(map_to_cta(a_full(slot), 0));
+    };
     auto publish_chunk = [&]() {                 // all of this warp's writes to the current A slot are done
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_full(ra.slot));
+      if (lane == 0) arrive_a_full(ra.slot);
       ra.advance<kASlots>();
     };
+    uint32_t meta_phase = 0;
     auto wait_slot = [&]() { mbar_wait(a_empty(ra.slot), ra.phase ^ 1, a.error_flag); };
 
-    for (int grp_i = cluster_id, it = 0; grp_i < n_groups; grp_i += n_clusters, ++it) {
-      const int tile = grp_i * (int)cs + (int)crank;
+    for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
+      const int tile = grp_i * CG + (int)crank;
       const int row0 = tile * kTileM;
       // ---------------- front-end: geometry of this tile's 128 points (threads 0..127, one point each) --------
       float px = 0.f, py = 0.f, pz = 0.f;
@@ -415,20 +501,31 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           for (int s = 0; s < kScales; ++s) my_scales |= scale_taps(p, s, sx, sy).any ? (1u << s) : 0u;
         }
       }
-      if (a.skip_zero) {
-        // OR the per-point scale bits over the tile -> chunk mask (one atomicOr per warp)
-        uint32_t wbits = __reduce_or_sync(0xffffffffu, my_scales);
-        if (wt == 0) mask_smem[it & 1] = 0ull;
-        named_bar_sync(1, kWorkerThreads);
-        if (lane == 0 && wbits) atomicOr((unsigned long long*)&mask_smem[it & 1], chunk_mask_for_scales(p, wbits, kz));
-      }
-      named_bar_sync(1, kWorkerThreads);          // sph_smem (and the mask) visible to all workers
       uint64_t mask = ~0ull;
       if (a.skip_zero) {
+        // Chunk mask of this tile GROUP = OR over the points of every CTA of the group (all roles of all CTAs must
+        // skip the same chunks).  Buffer (it&1) was zeroed one tile ago; each warp ORs its bits into the buffer of
+        // every CTA of the group and arrives on every CTA's meta barrier.
+        const uint32_t wbits = __reduce_or_sync(0xffffffffu, my_scales);
+        if (wt == 0) mask_smem[(it + 1) & 1] = 0ull;
+        if (lane == 0) {
+          const unsigned long long bits = chunk_mask_for_scales(p, wbits, kz);
+          const uint32_t maddr = smem_base + kSmemMask + 8u * (it & 1);
+          if constexpr (CG == 1) {
+            if (bits) atomicOr((unsigned long long*)&mask_smem[it & 1], bits);
+            mbar_arrive(meta_full);
+          } else {
+            for (uint32_t r = 0; r < 2; ++r) {
+              if (bits) atom_or_remote_u64(map_to_cta(maddr, r), bits);
+              mbar_arrive_remote(map_to_cta(meta_full, r));
+            }
+          }
+        }
+        mbar_wait_cluster(meta_full, meta_phase, a.error_flag);
+        meta_phase ^= 1;
         mask = mask_smem[it & 1];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(meta_full);    // release: producer + MMA issuer may read the mask
       }
+      named_bar_sync(1, kWorkerThreads);          // sph_smem visible to all workers
 
       // ---------------- L0: x chunk = [pe(39) | viewdir(3) | 0] as fp16 ---------------------------------------
       wait_slot();
@@ -552,7 +649,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           for (int cidx = 0; cidx < kHiddenChunks; ++cidx) {
             int slot = ra.slot + cidx;
             if (slot >= kASlots) slot -= kASlots;
-            mbar_arrive(a_full(slot));
+            arrive_a_full(slot);
           }
         }
         for (int cidx = 0; cidx < kHiddenChunks; ++cidx) ra.advance<kASlots>();
@@ -621,10 +718,10 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
   // ---- teardown -------------------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (cs > 1) cluster_sync_all();            // no CTA may exit while a peer can still signal its barriers
+  if (CG == 2) cluster_sync_all();           // no CTA may exit while its peer can still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc<CG>(tmem_base, kTmemCols);
   }
 }
 
@@ -746,14 +843,13 @@ static int num_sms() {
   return g_num_sms;
 }
 
-static int tc_cluster_size() {
-  static int cs = -1;
-  if (cs < 0) {
-    const char* e = getenv("SRF_TC_CLUSTER");
-    cs = e ? atoi(e) : 2;
-    if (cs != 1 && cs != 2 && cs != 4 && cs != 8) cs = 1;
+static int tc_cta_group() {
+  static int cg = -1;
+  if (cg < 0) {
+    const char* e = getenv("SRF_TC_CTA_GROUP");
+    cg = (e && atoi(e) == 1) ? 1 : 2;
   }
-  return cs;
+  return cg;
 }
 
 size_t tc_workspace_bytes(int d_latent, int n_points) {
@@ -769,7 +865,8 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
     return -2;                         // layers without an ACC-complete signal cannot be dumped
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc::point_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
+    cudaFuncSetAttribute(tc::point_mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
+    cudaFuncSetAttribute(tc::point_mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
     attr_set = true;
   }
   tc::KernelArgs a;
@@ -783,34 +880,33 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
   a.debug_layer = debug_layer; a.debug_acc = debug_acc;
   a.error_flag = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + (size_t)256 * tc::kTileM * kHidden * sizeof(float));
   cudaMemsetAsync(a.error_flag, 0, sizeof(int), st);
-  // Cluster size of the shared weight stream (1 = private stream per CTA).  Skipping zero chunks needs a per-tile
-  // chunk mask, which is CTA-private for now -> private streams in that mode.
-  int cs = tc_cluster_size();
-  if (a.skip_zero || a.n_tiles < 2 * cs) cs = 1;
+  // CTA pairs (cta_group::2, cluster of 2) by default; SRF_TC_CTA_GROUP=1 selects the single-CTA variant.
+  const int cg = (tc_cta_group() == 2 && a.n_tiles >= 2) ? 2 : 1;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(tc::kThreads);
   cfg.dynamicSmemBytes = tc::kSmemTotal + 1024;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int max_ctas = num_sms();
-  if (cs > 1) {
-    static int max_clusters[9] = {0};
-    if (!max_clusters[cs]) {
-      cfg.gridDim = dim3(num_sms() / cs * cs);
+  if (cg == 2) {
+    static int max_pairs = 0;
+    if (!max_pairs) {
+      cfg.gridDim = dim3(num_sms() / 2 * 2);
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, tc::point_mlp_tc_kernel, &cfg) != cudaSuccess || nc < 1) nc = num_sms() / cs / 2;
-      max_clusters[cs] = nc;
+      if (cudaOccupancyMaxActiveClusters(&nc, tc::point_mlp_tc_kernel<2>, &cfg) != cudaSuccess || nc < 1) nc = num_sms() / 2;
+      max_pairs = nc;
     }
-    max_ctas = max_clusters[cs] * cs;
+    max_ctas = max_pairs * 2;
   }
-  const int n_groups = (a.n_tiles + cs - 1) / cs;
-  int grid = n_groups * cs < max_ctas ? n_groups * cs : max_ctas;
-  if (grid > 256) grid = 256 / cs * cs;
+  const int n_groups = (a.n_tiles + cg - 1) / cg;
+  int grid = n_groups * cg < max_ctas ? n_groups * cg : max_ctas;
+  if (grid > 256) grid = 256;
   cfg.gridDim = dim3(grid);
-  cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel, p, a);
+  if (cg == 2) cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<2>, p, a);
+  else cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<1>, p, a);
   return 2;
 }
 
