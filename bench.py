@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--skip-zero-chunks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rays", type=int, default=0, help="diagnostics: use only the first N rays of the workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -216,6 +217,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg, pix_np, desc = workload(args.workload)
     cfg.tz = cfg.tz + 0.5 * rank                      # frame-per-GPU: every rank renders its own pose
+    if args.rays > 0:
+        sel = np.random.default_rng(3).permutation(pix_np.shape[0])[:args.rays]
+        pix_np = np.ascontiguousarray(pix_np[np.sort(sel)])
+        desc += " [diagnostic subset: %d rays]" % pix_np.shape[0]
     R = pix_np.shape[0]
     pm, pg = synth.make_model_params(cfg)
     to_t = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}

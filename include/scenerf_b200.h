@@ -173,6 +173,10 @@ int srf_debug_tc_layer(const srf_config* cfg, const srf_pyramid* pyr, const srf_
 void srf_set_profiling(int on);
 int srf_last_mlp_ms(float* gauss_ms, float* main_ms);
 
+/* Diagnostic: non-zero once the tensor-core kernel's mbarrier watchdog fired (readable even after the resulting
+ * device trap): 0x40000000 | warp << 24 | (barrier smem offset) << 4 | parity. */
+int srf_debug_watchdog_flag(void);
+
 /* Number of kernels the last srf_render_rays / srf_predict call on this thread launched (bench "gpu_launches"). */
 int srf_last_launch_count(void);
 

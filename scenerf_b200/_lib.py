@@ -59,6 +59,7 @@ SYMBOLS = {
     "srf_last_error": (C.c_char_p, []),
     "srf_last_launch_count": (C.c_int, []),
     "srf_sizeof": (C.c_size_t, [C.c_int]),
+    "srf_debug_watchdog_flag": (C.c_int, []),
     "srf_set_profiling": (None, [C.c_int]),
     "srf_last_mlp_ms": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "srf_pyramid_bytes": (C.c_size_t, [C.POINTER(C.c_int)] * 3),

@@ -23,7 +23,7 @@ int fail(int code, const char* fmt, ...) {
 
 int check_cuda(const char* what) {
   const cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(SRF_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(SRF_E_CUDA, "%s: %s (tc watchdog flag 0x%x)", what, cudaGetErrorString(e), srf::tc_watchdog_flag());
   return SRF_OK;
 }
 
@@ -202,6 +202,7 @@ extern "C" {
 int srf_abi_version(void) { return SRF_ABI_VERSION; }
 const char* srf_last_error(void) { return g_err; }
 int srf_last_launch_count(void) { return g_launches; }
+int srf_debug_watchdog_flag(void) { return srf::tc_watchdog_flag(); }
 void srf_set_profiling(int on) { g_profiling = on != 0; }
 int srf_last_mlp_ms(float* gauss_ms, float* main_ms) {
   float* dst[2] = {gauss_ms, main_ms};

@@ -32,6 +32,8 @@ int run_point_mlp_tc(const DevParams& p, const srf_mlp_weights& w, const float* 
                      int n_per, float* raw_out, int32_t* dbg_sphere, int flags, void* workspace, size_t ws_bytes,
                      cudaStream_t st);
 
+// non-zero after the kernel's mbarrier watchdog fired: 0x40000000 | warp<<24 | (barrier smem offset)<<4 | parity
+int tc_watchdog_flag();
 // diagnostic: stop every tile after `debug_layer` (1,2,4,5,7,8,9,10 -- see the tile program in mlp_tc.cu) and dump the
 // raw fp32 accumulator (n_tiles*128, 512) to debug_acc
 int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n,

@@ -30,6 +30,7 @@
 // warp 1 relays its weight-full barriers to the leader, and the leader's tcgen05.commit multicasts the "empty" /
 // "accumulator complete" signals to both CTAs.  CG = 1 is the single-CTA variant (M = 128, N = 128).
 #include <cuda_fp16.h>
+#include <cstdio>
 #include <cstdlib>
 #include "kernels.cuh"
 
@@ -84,6 +85,7 @@ struct KernelArgs {
   int debug_layer;         // -1, or: stop every tile after this layer's ACC is complete and dump it
   float* debug_acc;        // (n_tiles*128, 512)
   int* error_flag;         // set to non-zero by the watchdog
+  unsigned long long* prof; // optional (SRF_TC_PROF=1): per-CTA cycle counters, 16 per CTA
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -385,6 +387,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       // ===================================== MMA issuer (leader CTA) ===========================================
       Ring ra, rb;
       uint32_t meta_phase = 0;
+      long long wa = 0, wb = 0;                  // cycles the issuer waited for A chunks / weight images
+      const bool prof_on = a.prof != nullptr;
       const uint32_t idesc_main = make_idesc(kTileM * CG, kMmaN);
       const uint32_t idesc_out = make_idesc(kTileM * CG, kOutN);
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
@@ -401,12 +405,16 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           bool first = kLayers[l].fresh;           // the first executed chunk of a fresh layer overwrites ACC
           for (int c = 0; c < nc; ++c) {
             if (!chunk_active(l, c, mask)) continue;
+            long long t0 = prof_on ? clock64() : 0;
             mbar_wait_cluster(a_full(ra.slot), ra.phase, a.error_flag);
+            if (prof_on) wa += clock64() - t0;
             tc_fence_after();
             const uint64_t adesc = make_desc_sw128(smem_base + kSmemA + ra.slot * kASlotBytes);
             const int nh = is_out ? 1 : kImgPerChunk;
             for (int h = 0; h < nh; ++h) {
+              t0 = prof_on ? clock64() : 0;
               mbar_wait_cluster(b_full(rb.slot), rb.phase, a.error_flag);
+              if (prof_on) wb += clock64() - t0;
               tc_fence_after();
               const uint64_t bdesc = make_desc_sw128(smem_base + kSmemB + rb.slot * kBSlotBytes);
 #pragma unroll
@@ -426,6 +434,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         }
         if (a.skip_zero) meta_phase ^= 1;
       }
+      if (prof_on) { a.prof[(size_t)blockIdx.x * 16 + 8] = (unsigned long long)wa; a.prof[(size_t)blockIdx.x * 16 + 9] = (unsigned long long)wb; }
     } else if (CG == 2 && lane == 0 && !leader) {
       // ===================================== weight-full relay (peer CTA) ======================================
       // walks the same image sequence as the producer; when a local image has landed, arrives on the leader's
@@ -480,6 +489,13 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     };
     uint32_t meta_phase = 0;
     auto wait_slot = [&]() { mbar_wait(a_empty(ra.slot), ra.phase ^ 1, a.error_flag); };
+    // cycle accounting (one thread per CTA: first worker lane): 0 front-end, 1 gather passes, 2 waiting for ACC,
+    // 3 epilogue bodies, 4 whole kernel
+    const bool prof_on = (a.prof != nullptr) && (wt == 0);
+    long long pc[5] = {0, 0, 0, 0, 0};
+    long long pt = prof_on ? clock64() : 0;
+    const long long pt_start = pt;
+    auto lap = [&](int idx) { if (prof_on) { const long long t = clock64(); pc[idx] += t - pt; pt = t; } };
 
     for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
       const int tile = grp_i * CG + (int)crank;
@@ -602,9 +618,11 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       // ---------------- epilogue: ACC (TMEM) -> [+bias (+h)] -> (scratch) -> relu -> fp16 A chunks -------------
       //   bias_idx: which header vector; use_h: add the fp32 hidden state from scratch; write_h: store it back
       auto epilogue_to_act = [&](int bias_idx, bool use_h, bool write_h) {
+        lap(1);
         mbar_wait(acc_full, acc_phase, a.error_flag);
         acc_phase ^= 1;
         tc_fence_after();
+        lap(2);
         const float4* b4 = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden);
         // this warp writes A slots of chunks [4*col_half, 4*col_half+4); slots of an epilogue are ra.slot+0..7
         for (int grp = 0; grp < 8; ++grp) {
@@ -653,6 +671,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           }
         }
         for (int cidx = 0; cidx < kHiddenChunks; ++cidx) ra.advance<kASlots>();
+        lap(3);
       };
 
       auto dump_acc = [&]() {                     // debug: raw accumulator of the current layer
@@ -680,6 +699,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         if (a.debug_layer == l) { dump_acc(); stop = true; }
         return stop;
       };
+      lap(0);
       gather_pass();                                              // L1 lin_z0
       if (after_layer(1)) continue;
       for (int b = 0; b < SRF_NUM_BLOCKS && !stop; ++b) {
@@ -697,9 +717,11 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       epilogue_to_act(/*bias*/ 6, true, false);                                 // E3 -> feeds lin_out
       if (after_layer(10)) continue;
       // ---------------- E4: out = ACC[:, :d_out] + b_out ------------------------------------------------------
+      lap(1);
       mbar_wait(acc_full, acc_phase, a.error_flag);
       acc_phase ^= 1;
       tc_fence_after();
+      lap(2);
       if (col_half == 0) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16), v);   // 32 columns; only the first 16 are meaningful
@@ -712,6 +734,12 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
+      lap(3);
+    }
+    if (prof_on) {
+      unsigned long long* dst = a.prof + (size_t)blockIdx.x * 16;
+      for (int i = 0; i < 4; ++i) dst[i] = (unsigned long long)pc[i];
+      dst[4] = (unsigned long long)(clock64() - pt_start);
     }
   }
 
@@ -832,6 +860,10 @@ int pack_weights_tc(const srf_mlp_weights& w, void* dst, size_t bytes, cudaStrea
   return 0;
 }
 
+static int* g_wd_host = nullptr;
+static int* g_wd_dev = nullptr;
+int tc_watchdog_flag() { return g_wd_host ? *g_wd_host : 0; }
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -878,8 +910,22 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
   a.raw_out = raw_out; a.d_out = w.d_out; a.dbg_sphere = dbg_sphere;
   a.skip_zero = (flags & SRF_FLAG_SKIP_ZERO_CHUNKS) ? 1 : 0;
   a.debug_layer = debug_layer; a.debug_acc = debug_acc;
-  a.error_flag = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + (size_t)256 * tc::kTileM * kHidden * sizeof(float));
-  cudaMemsetAsync(a.error_flag, 0, sizeof(int), st);
+  // watchdog flag in mapped pinned host memory: still readable after a device-side trap killed the context
+  if (!g_wd_host) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&g_wd_host), sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+      *g_wd_host = 0;
+      cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_wd_dev), g_wd_host, 0);
+    }
+  }
+  a.error_flag = g_wd_dev;
+  static const bool prof_env = getenv("SRF_TC_PROF") != nullptr;
+  static unsigned long long* prof_dev = nullptr;
+  a.prof = nullptr;
+  if (prof_env) {
+    if (!prof_dev) cudaMalloc(&prof_dev, 256 * 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(prof_dev, 0, 256 * 16 * sizeof(unsigned long long), st);
+    a.prof = prof_dev;
+  }
   // CTA pairs (cta_group::2, cluster of 2) by default; SRF_TC_CTA_GROUP=1 selects the single-CTA variant.
   const int cg = (tc_cta_group() == 2 && a.n_tiles >= 2) ? 2 : 1;
   cudaLaunchConfig_t cfg = {};
@@ -907,6 +953,17 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
   cfg.gridDim = dim3(grid);
   if (cg == 2) cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<2>, p, a);
   else cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<1>, p, a);
+  if (prof_env) {            // diagnostics only: synchronises and prints mean per-CTA cycle counters
+    static unsigned long long host[256 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, prof_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    double m[16] = {0};
+    for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) m[i] += (double)host[b * 16 + i] / grid;
+    const double tiles = (double)((n_groups + grid / cg - 1) / (grid / cg));
+    fprintf(stderr, "[srf tc prof] cg=%d grid=%d tiles/CTA=%.0f  per-tile kcycles: total %.1f | worker: front %.1f gather %.1f wait_acc %.1f epilogue %.1f | issuer(leader avg x%d): wait_A %.1f wait_B %.1f\n",
+            cg, grid, tiles, m[4] / tiles / 1e3, m[0] / tiles / 1e3, m[1] / tiles / 1e3, m[2] / tiles / 1e3, m[3] / tiles / 1e3,
+            cg, m[8] * cg / tiles / 1e3, m[9] * cg / tiles / 1e3);
+  }
   return 2;
 }
 
