@@ -148,7 +148,9 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default .release.cta semantics: the data this guards was already handed to the async proxy by
+  // fence.proxy.async; a .release.cluster here compiles to MEMBAR.ALL.GPU and drains every global store first
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void atom_or_remote_u64(uint32_t cluster_addr, unsigned long long v) {
   asm volatile("red.relaxed.cluster.shared::cluster.or.b64 [%0], %1;" ::"r"(cluster_addr), "l"(v) : "memory");
@@ -239,7 +241,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  // no "memory" clobber on purpose: global loads of the next item may be hoisted above this store (volatile asm
+  // statements still keep their order relative to the fences / arrives that publish the tile)
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
@@ -324,7 +328,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     // B-full: the local producer's arrive.expect_tx (+ its bytes); on the leader of a pair also the peer's relay
     for (int s = 0; s < kBSlots; ++s) { mbar_init(b_full(s), (CG == 2 && leader) ? 2 : 1); mbar_init(b_empty(s), 1); }
     mbar_init(acc_full, 1);
-    mbar_init(meta_full, kWorkerWarps * CG);
+    mbar_init(meta_full, kWorkerWarps);
     mask_smem[0] = 0ull; mask_smem[1] = 0ull;
     fence_barrier_init();
   }
@@ -359,7 +363,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           const int nc = layer_chunks(l, kz);
           const bool is_out = kLayers[l].is_out;
           if (kLayers[l].chunks_is_kz && !have_mask) {
-            mbar_wait_cluster(meta_full, meta_phase, a.error_flag);     // this tile group's chunk mask is published
+            mbar_wait(meta_full, meta_phase, a.error_flag);     // this tile group's chunk mask is published
             mask = mask_smem[it & 1];
             have_mask = true;
           }
@@ -398,7 +402,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           const int nc = layer_chunks(l, kz);
           const bool is_out = kLayers[l].is_out;
           if (kLayers[l].chunks_is_kz && !have_mask) {
-            mbar_wait_cluster(meta_full, meta_phase, a.error_flag);
+            mbar_wait(meta_full, meta_phase, a.error_flag);
             mask = mask_smem[it & 1];
             have_mask = true;
           }
@@ -411,21 +415,26 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             tc_fence_after();
             const uint64_t adesc = make_desc_sw128(smem_base + kSmemA + ra.slot * kASlotBytes);
             const int nh = is_out ? 1 : kImgPerChunk;
+            // all weight images of this chunk first, then the MMAs back to back, then the releases
+            int bslot[kQuarters];
             for (int h = 0; h < nh; ++h) {
               t0 = prof_on ? clock64() : 0;
               mbar_wait_cluster(b_full(rb.slot), rb.phase, a.error_flag);
               if (prof_on) wb += clock64() - t0;
-              tc_fence_after();
-              const uint64_t bdesc = make_desc_sw128(smem_base + kSmemB + rb.slot * kBSlotBytes);
+              bslot[h] = rb.slot;
+              rb.advance<kBSlots>();
+            }
+            tc_fence_after();
+            for (int h = 0; h < nh; ++h) {
+              const uint64_t bdesc = make_desc_sw128(smem_base + kSmemB + bslot[h] * kBSlotBytes);
 #pragma unroll
               for (int k = 0; k < kChunkK / 16; ++k) {
                 // +32 bytes per UMMA_K=16 fp16 inside the swizzle atom row: start address field += 2
                 umma_f16<CG>(tmem_base + (uint32_t)(h * kMmaN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
                              is_out ? idesc_out : idesc_main, (first && k == 0) ? 0u : 1u);
               }
-              umma_commit<CG>(b_empty(rb.slot));
-              rb.advance<kBSlots>();
             }
+            for (int h = 0; h < nh; ++h) umma_commit<CG>(b_empty(bslot[h]));
             first = false;
             umma_commit<CG>(a_empty(ra.slot));
             ra.advance<kASlots>();
@@ -447,7 +456,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         for (int l = 0; l <= last_layer; ++l) {
           const int nc = layer_chunks(l, kz);
           if (kLayers[l].chunks_is_kz && !have_mask) {
-            mbar_wait_cluster(meta_full, meta_phase, a.error_flag);
+            mbar_wait(meta_full, meta_phase, a.error_flag);
             mask = mask_smem[it & 1];
             have_mask = true;
           }
@@ -501,43 +510,40 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       const int tile = grp_i * CG + (int)crank;
       const int row0 = tile * kTileM;
       // ---------------- front-end: geometry of this tile's 128 points (threads 0..127, one point each) --------
+      // With zero-chunk skipping in a CTA pair, threads 128..255 (idle here otherwise) run the same geometry for the
+      // PEER's tile, so that both CTAs derive the identical union chunk mask locally (no cross-CTA exchange).
       float px = 0.f, py = 0.f, pz = 0.f;
       uint32_t my_scales = 0;
-      if (wt < kTileM) {
-        const int gi = row0 + wt;
-        int sx = kSphereInvalid, sy = kSphereInvalid;
-        if (gi < a.n) {
-          px = a.pts[(size_t)gi * 3 + 0]; py = a.pts[(size_t)gi * 3 + 1]; pz = a.pts[(size_t)gi * 3 + 2];
-          point_to_sphere(p, px, py, pz, sx, sy);
-          if (a.dbg_sphere) { a.dbg_sphere[(size_t)gi * 2 + 0] = sx; a.dbg_sphere[(size_t)gi * 2 + 1] = sy; }
-        }
-        sph_smem[wt] = make_int2(sx, sy);
-        if (a.skip_zero) {
+      {
+        const bool own = wt < kTileM;
+        const int trow = own ? wt : wt - kTileM;
+        const int ttile = own ? tile : (grp_i * CG + (1 - (int)crank));
+        if (own || (CG == 2 && a.skip_zero)) {
+          const int gi = ttile * kTileM + trow;
+          int sx = kSphereInvalid, sy = kSphereInvalid;
+          if (gi < a.n) {
+            px = a.pts[(size_t)gi * 3 + 0]; py = a.pts[(size_t)gi * 3 + 1]; pz = a.pts[(size_t)gi * 3 + 2];
+            point_to_sphere(p, px, py, pz, sx, sy);
+            if (own && a.dbg_sphere) { a.dbg_sphere[(size_t)gi * 2 + 0] = sx; a.dbg_sphere[(size_t)gi * 2 + 1] = sy; }
+          }
+          if (own) sph_smem[wt] = make_int2(sx, sy);
+          if (a.skip_zero) {
 #pragma unroll
-          for (int s = 0; s < kScales; ++s) my_scales |= scale_taps(p, s, sx, sy).any ? (1u << s) : 0u;
+            for (int s = 0; s < kScales; ++s) my_scales |= scale_taps(p, s, sx, sy).any ? (1u << s) : 0u;
+          }
         }
       }
       uint64_t mask = ~0ull;
       if (a.skip_zero) {
-        // Chunk mask of this tile GROUP = OR over the points of every CTA of the group (all roles of all CTAs must
-        // skip the same chunks).  Buffer (it&1) was zeroed one tile ago; each warp ORs its bits into the buffer of
-        // every CTA of the group and arrives on every CTA's meta barrier.
+        // chunk mask of this tile group: buffer (it&1) was zeroed one tile ago
         const uint32_t wbits = __reduce_or_sync(0xffffffffu, my_scales);
         if (wt == 0) mask_smem[(it + 1) & 1] = 0ull;
         if (lane == 0) {
           const unsigned long long bits = chunk_mask_for_scales(p, wbits, kz);
-          const uint32_t maddr = smem_base + kSmemMask + 8u * (it & 1);
-          if constexpr (CG == 1) {
-            if (bits) atomicOr((unsigned long long*)&mask_smem[it & 1], bits);
-            mbar_arrive(meta_full);
-          } else {
-            for (uint32_t r = 0; r < 2; ++r) {
-              if (bits) atom_or_remote_u64(map_to_cta(maddr, r), bits);
-              mbar_arrive_remote(map_to_cta(meta_full, r));
-            }
-          }
+          if (bits) atomicOr((unsigned long long*)&mask_smem[it & 1], bits);
+          mbar_arrive(meta_full);
         }
-        mbar_wait_cluster(meta_full, meta_phase, a.error_flag);
+        mbar_wait(meta_full, meta_phase, a.error_flag);
         meta_phase ^= 1;
         mask = mask_smem[it & 1];
       }
@@ -625,32 +631,43 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         lap(2);
         const float4* b4 = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden);
         // this warp writes A slots of chunks [4*col_half, 4*col_half+4); slots of an epilogue are ra.slot+0..7
+        // The fp32 hidden state comes from the L2-resident scratch: the 8 float4 of group g+1 are requested before
+        // group g is processed (software prefetch in registers), so one L2 latency is exposed per phase, not per group.
+        float4 hn[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          hn[j] = use_h ? scratch4[(size_t)((col_half * 256 >> 2) + j) * kTileM + erow] : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int grp = 0; grp < 8; ++grp) {
           const int col = col_half * 256 + grp * 32;
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, v);
-          tmem_ld_wait();
+          tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, v);      // asynchronous until the wait
+          float4 hh[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) hh[j] = hn[j];
+          if (use_h && grp < 7) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hn[j] = scratch4[(size_t)(((col + 32) >> 2) + j) * kTileM + erow];
+          }
           const int chunk = col >> 6;
           int slot = ra.slot + chunk;
           uint32_t ph = ra.phase;
           if (slot >= kASlots) { slot -= kASlots; ph ^= 1; }
           if ((grp & 1) == 0) mbar_wait(a_empty(slot), ph ^ 1, a.error_flag);
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
+          tmem_ld_wait();
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {                        // 4 granules of 8 columns
             float h[8];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-              const int c4 = (col >> 2) + gq * 2 + half;          // float4 column index
-              const float4 bb = __ldg(b4 + c4);
-              float4 hh = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (use_h) hh = scratch4[(size_t)c4 * kTileM + erow];
+              const int j = gq * 2 + half;
+              const float4 bb = __ldg(b4 + (col >> 2) + j);       // 16 KB bias header: L1-resident broadcast load
               float4 r;
-              r.x = __uint_as_float(v[gq * 8 + half * 4 + 0]) + bb.x + hh.x;
-              r.y = __uint_as_float(v[gq * 8 + half * 4 + 1]) + bb.y + hh.y;
-              r.z = __uint_as_float(v[gq * 8 + half * 4 + 2]) + bb.z + hh.z;
-              r.w = __uint_as_float(v[gq * 8 + half * 4 + 3]) + bb.w + hh.w;
-              if (write_h) scratch4[(size_t)c4 * kTileM + erow] = r;
+              r.x = __uint_as_float(v[j * 4 + 0]) + bb.x + hh[j].x;
+              r.y = __uint_as_float(v[j * 4 + 1]) + bb.y + hh[j].y;
+              r.z = __uint_as_float(v[j * 4 + 2]) + bb.z + hh[j].z;
+              r.w = __uint_as_float(v[j * 4 + 3]) + bb.w + hh[j].w;
+              if (write_h) scratch4[(size_t)((col >> 2) + j) * kTileM + erow] = r;
               h[half * 4 + 0] = fmaxf(r.x, 0.f); h[half * 4 + 1] = fmaxf(r.y, 0.f);
               h[half * 4 + 2] = fmaxf(r.z, 0.f); h[half * 4 + 3] = fmaxf(r.w, 0.f);
             }
