@@ -237,6 +237,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -501,7 +502,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     // cycle accounting (one thread per CTA: first worker lane): 0 front-end, 1 gather passes, 2 waiting for ACC,
     // 3 epilogue bodies, 4 whole kernel
     const bool prof_on = (a.prof != nullptr) && (wt == 0);
-    long long pc[5] = {0, 0, 0, 0, 0};
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 5: E2-type, 6: E3, 7: time blocked in wait_slot during gather
     long long pt = prof_on ? clock64() : 0;
     const long long pt_start = pt;
     auto lap = [&](int idx) { if (prof_on) { const long long t = clock64(); pc[idx] += t - pt; pt = t; } };
@@ -526,7 +527,25 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             point_to_sphere(p, px, py, pz, sx, sy);
             if (own && a.dbg_sphere) { a.dbg_sphere[(size_t)gi * 2 + 0] = sx; a.dbg_sphere[(size_t)gi * 2 + 1] = sy; }
           }
-          if (own) sph_smem[wt] = make_int2(sx, sy);
+          if (own) {
+            sph_smem[wt] = make_int2(sx, sy);
+            // warm L2 with the taps this row will gather from the (usually in-bounds) fine scales: the gather runs
+            // thousands of cycles later and then sees L2 instead of HBM latency
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const Taps tp = scale_taps(p, s, sx, sy);
+              if (tp.any) {
+                const int bytes = p.C[s] * 4;
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  if (tp.off[t] >= 0) {
+                    const char* base = reinterpret_cast<const char*>(p.feat[s] + tp.off[t]);
+                    for (int b = 0; b < bytes; b += 128) prefetch_l2(base + b);
+                    prefetch_l2(base + bytes - 4);
+                  }
+              }
+            }
+          }
           if (a.skip_zero) {
 #pragma unroll
             for (int s = 0; s < kScales; ++s) my_scales |= scale_taps(p, s, sx, sy).any ? (1u << s) : 0u;
@@ -590,32 +609,57 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             }
             cur_scale = s;
           }
-          wait_slot();
+          {
+            const long long tw = prof_on ? clock64() : 0;
+            wait_slot();
+            if (prof_on) pc[7] += clock64() - tw;
+          }
           const uint32_t slot_addr = smem_base + kSmemA + ra.slot * kASlotBytes;
+          // two items at a time: their 16 tap loads (128-bit) are all requested before the first one is consumed,
+          // so a chunk costs two memory round trips instead of four
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = (wt >> 3) + 32 * i;
-            float acc[8];
+          for (int ib = 0; ib < 4; ib += 2) {
+            float4 v[2][4][2];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-            if (s >= 0 && taps[i].any) {
-              const float* f = p.feat[s] + (ch - p.ch_off[s]);
+            for (int u = 0; u < 2; ++u) {
+              const Taps& tp = taps[ib + u];
+              const bool live = (s >= 0) && tp.any;
+              const float* f = live ? p.feat[s] + (ch - p.ch_off[s]) : nullptr;
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                if (taps[i].off[t] >= 0) {
-                  const float4 v0 = __ldg(reinterpret_cast<const float4*>(f + taps[i].off[t]));
-                  const float4 v1 = __ldg(reinterpret_cast<const float4*>(f + taps[i].off[t]) + 1);
-                  const float w = taps[i].w[t];
-                  // out = ((v_nw*nw + v_ne*ne) + v_sw*sw) + v_se*se : separate roundings like ATen's CPU kernel
-                  acc[0] = fadd(acc[0], fmul(v0.x, w)); acc[1] = fadd(acc[1], fmul(v0.y, w));
-                  acc[2] = fadd(acc[2], fmul(v0.z, w)); acc[3] = fadd(acc[3], fmul(v0.w, w));
-                  acc[4] = fadd(acc[4], fmul(v1.x, w)); acc[5] = fadd(acc[5], fmul(v1.y, w));
-                  acc[6] = fadd(acc[6], fmul(v1.z, w)); acc[7] = fadd(acc[7], fmul(v1.w, w));
+                if (live && tp.off[t] >= 0) {
+                  v[u][t][0] = __ldg(reinterpret_cast<const float4*>(f + tp.off[t]));
+                  v[u][t][1] = __ldg(reinterpret_cast<const float4*>(f + tp.off[t]) + 1);
+                } else {
+                  v[u][t][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  v[u][t][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
               }
             }
-            sts128(slot_addr + sw128_offset(row, g), pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
-                   pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]));
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const Taps& tp = taps[ib + u];
+              const int row = (wt >> 3) + 32 * (ib + u);
+              float acc[8];
+              // out = ((v_nw*nw + v_ne*ne) + v_sw*sw) + v_se*se : separate roundings like ATen's CPU kernel
+              // (an out-of-range tap contributes an exact +0)
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float w = tp.w[t];
+                const float4 a0 = v[u][t][0], a1 = v[u][t][1];
+                if (t == 0) {
+                  acc[0] = fmul(a0.x, w); acc[1] = fmul(a0.y, w); acc[2] = fmul(a0.z, w); acc[3] = fmul(a0.w, w);
+                  acc[4] = fmul(a1.x, w); acc[5] = fmul(a1.y, w); acc[6] = fmul(a1.z, w); acc[7] = fmul(a1.w, w);
+                } else {
+                  acc[0] = fadd(acc[0], fmul(a0.x, w)); acc[1] = fadd(acc[1], fmul(a0.y, w));
+                  acc[2] = fadd(acc[2], fmul(a0.z, w)); acc[3] = fadd(acc[3], fmul(a0.w, w));
+                  acc[4] = fadd(acc[4], fmul(a1.x, w)); acc[5] = fadd(acc[5], fmul(a1.y, w));
+                  acc[6] = fadd(acc[6], fmul(a1.z, w)); acc[7] = fadd(acc[7], fmul(a1.w, w));
+                }
+              }
+              sts128(slot_addr + sw128_offset(row, g), pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
+                     pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]));
+            }
           }
           publish_chunk();
         }
@@ -688,7 +732,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           }
         }
         for (int cidx = 0; cidx < kHiddenChunks; ++cidx) ra.advance<kASlots>();
-        lap(3);
+        lap(write_h ? 3 : (use_h ? 6 : 5));
       };
 
       auto dump_acc = [&]() {                     // debug: raw accumulator of the current layer
@@ -757,6 +801,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       unsigned long long* dst = a.prof + (size_t)blockIdx.x * 16;
       for (int i = 0; i < 4; ++i) dst[i] = (unsigned long long)pc[i];
       dst[4] = (unsigned long long)(clock64() - pt_start);
+      dst[5] = (unsigned long long)pc[5]; dst[6] = (unsigned long long)pc[6]; dst[7] = (unsigned long long)pc[7];
     }
   }
 
@@ -977,9 +1022,9 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
     double m[16] = {0};
     for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) m[i] += (double)host[b * 16 + i] / grid;
     const double tiles = (double)((n_groups + grid / cg - 1) / (grid / cg));
-    fprintf(stderr, "[srf tc prof] cg=%d grid=%d tiles/CTA=%.0f  per-tile kcycles: total %.1f | worker: front %.1f gather %.1f wait_acc %.1f epilogue %.1f | issuer(leader avg x%d): wait_A %.1f wait_B %.1f\n",
-            cg, grid, tiles, m[4] / tiles / 1e3, m[0] / tiles / 1e3, m[1] / tiles / 1e3, m[2] / tiles / 1e3, m[3] / tiles / 1e3,
-            cg, m[8] * cg / tiles / 1e3, m[9] * cg / tiles / 1e3);
+    fprintf(stderr, "[srf tc prof] cg=%d grid=%d tiles/CTA=%.0f  per-tile kcycles: total %.1f | worker: front %.1f gather %.1f (blocked on slots %.1f) wait_acc %.1f epi E1x3 %.1f E2x3 %.1f E3 %.1f | issuer(leader avg x%d): wait_A %.1f wait_B %.1f\n",
+            cg, grid, tiles, m[4] / tiles / 1e3, m[0] / tiles / 1e3, m[1] / tiles / 1e3, m[7] / tiles / 1e3, m[2] / tiles / 1e3,
+            m[3] / tiles / 1e3, m[5] / tiles / 1e3, m[6] / tiles / 1e3, cg, m[8] * cg / tiles / 1e3, m[9] * cg / tiles / 1e3);
   }
   return 2;
 }

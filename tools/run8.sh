@@ -1,0 +1,13 @@
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_tc_layers.py -x -q > gpurun_out/run8_layers.log 2>&1; echo "layers rc=$?"; tail -2 gpurun_out/run8_layers.log
+export SRF_TC_PROF=1
+for skip in 0 1; do
+  echo "== prof cg=2 skip=$skip"
+  timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --rays 60000 --skip-zero-chunks $skip 2>&1 >/dev/null | grep -E "srf tc prof|Error|error" | tail -1
+done
+unset SRF_TC_PROF
+for skip in 0 1; do
+timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --skip-zero-chunks $skip > gpurun_out/run8_bench_s$skip.json 2> gpurun_out/run8_bench_s$skip.err; echo "bench skip=$skip rc=$?"
+python -c "
+import json;d=json.load(open('gpurun_out/run8_bench_s$skip.json'));print('skip=$skip', round(d['value']), round(d['ms_per_step'],1), round(d['roofline']['frac'],3), d['clocks'])" || tail -5 gpurun_out/run8_bench_s$skip.err
+done
