@@ -117,6 +117,7 @@ __device__ __forceinline__ void positional_encoding(float x, float y, float z, S
 struct Taps {
   int off[4];     // element offset of the tap's first channel in the HWC map, or -1 if the tap is out of range
   float w[4];     // nw, ne, sw, se
+  float fx, fy;   // fractional x / y position (w and n below): w[] = {(1-fy)(1-fx), (1-fy)fx, fy(1-fx), fy fx}
   bool any;
 };
 
@@ -135,6 +136,7 @@ __device__ __forceinline__ Taps scale_taps(const DevParams& p, int s, int sx, in
   const float n = fsub(iy, yn), so = fsub(1.0f, n);
   const int x0 = (int)xw, y0 = (int)yn;
   t.w[0] = fmul(so, e); t.w[1] = fmul(so, w); t.w[2] = fmul(n, e); t.w[3] = fmul(n, w);
+  t.fx = w; t.fy = n;
   t.any = false;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {

@@ -235,6 +235,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -302,7 +311,7 @@ __device__ __forceinline__ uint64_t chunk_mask_for_scales(const DevParams& p, ui
 // ---------------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int CG>
+template <int CG, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
 point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__ KernelArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -393,7 +402,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       Ring ra, rb;
       uint32_t meta_phase = 0;
       long long wa = 0, wb = 0;                  // cycles the issuer waited for A chunks / weight images
-      const bool prof_on = a.prof != nullptr;
+      const bool prof_on = PROF && a.prof != nullptr;
       const uint32_t idesc_main = make_idesc(kTileM * CG, kMmaN);
       const uint32_t idesc_out = make_idesc(kTileM * CG, kOutN);
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
@@ -501,11 +510,13 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     auto wait_slot = [&]() { mbar_wait(a_empty(ra.slot), ra.phase ^ 1, a.error_flag); };
     // cycle accounting (one thread per CTA: first worker lane): 0 front-end, 1 gather passes, 2 waiting for ACC,
     // 3 epilogue bodies, 4 whole kernel
-    const bool prof_on = (a.prof != nullptr) && (wt == 0);
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 5: E2-type, 6: E3, 7: time blocked in wait_slot during gather
+    const bool prof_on = PROF && (a.prof != nullptr) && (wt == 0);
+    long long pc[PROF ? 8 : 1] = {0};             // 5: E2-type, 6: E3, 7: time blocked in wait_slot during gather
     long long pt = prof_on ? clock64() : 0;
     const long long pt_start = pt;
-    auto lap = [&](int idx) { if (prof_on) { const long long t = clock64(); pc[idx] += t - pt; pt = t; } };
+    auto lap = [&](int idx) {
+      if constexpr (PROF) { if (prof_on) { const long long t = clock64(); pc[idx] += t - pt; pt = t; } }
+    };
 
     for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
       const int tile = grp_i * CG + (int)crank;
@@ -590,10 +601,16 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
 
       // ---------------- gather pass: produces the KZ latent chunks of one lin_z layer --------------------------
       // thread -> 4 items per chunk: rows (wt/8) + 32*i, granule (8 channels = 16 B of fp16) g = wt % 8
+      // thread -> 4 items per chunk: rows (wt/8) + 32*i, granule (8 channels = 16 B of fp16) g = wt % 8.
+      // Per row only (element offset of the north-west tap, x/y fractional weights, 4 validity bits) is kept in
+      // registers; the 4 tap weights are re-derived (same products as scale_taps) when a chunk is gathered.
       auto gather_pass = [&]() {
         const int g = wt & 7;
         int cur_scale = -1;
-        Taps taps[4];
+        int t_off[4];              // offset of tap 0 (may be "virtual" when tap 0 itself is out of range)
+        uint32_t t_ok[4];          // bit t = tap t in range
+        float t_w[4], t_n[4];      // fractional x / y weights (w, n of scale_taps)
+        int dxo = 0, dyo = 0;      // element strides to the east / south tap
         for (int c = 0; c < kz; ++c) {
           if (!((mask >> c) & 1ull)) continue;
           const int ch = c * kChunkK + g * 8;                     // first of this thread's 8 channels
@@ -602,34 +619,52 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           for (int i = 0; i < kScales; ++i)
             if (ch >= p.ch_off[i] && ch < p.ch_off[i + 1]) s = i;
           if (s >= 0 && s != cur_scale) {
+            dxo = p.C[s]; dyo = p.W[s] * p.C[s];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int2 sp = sph_smem[(wt >> 3) + 32 * i];
-              taps[i] = scale_taps(p, s, sp.x, sp.y);
+              const Taps tp = scale_taps(p, s, sp.x, sp.y);
+              t_ok[i] = (tp.off[0] >= 0 ? 1u : 0u) | (tp.off[1] >= 0 ? 2u : 0u) | (tp.off[2] >= 0 ? 4u : 0u) | (tp.off[3] >= 0 ? 8u : 0u);
+              // off[t] = off0 + (t&1)*dxo + (t>>1)*dyo for in-range taps -> recover off0 from any valid tap
+              int o0 = 0;
+              if (tp.off[0] >= 0) o0 = tp.off[0];
+              else if (tp.off[1] >= 0) o0 = tp.off[1] - dxo;
+              else if (tp.off[2] >= 0) o0 = tp.off[2] - dyo;
+              else if (tp.off[3] >= 0) o0 = tp.off[3] - dxo - dyo;
+              t_off[i] = o0;
+              // w[1] = so*w, w[0] = so*e ... keep (w, n): ne/nw = w/e split of the x axis, sw/nw = n/so of the y axis
+              t_w[i] = tp.fx; t_n[i] = tp.fy;
             }
             cur_scale = s;
           }
-          {
+          if constexpr (PROF) {
             const long long tw = prof_on ? clock64() : 0;
             wait_slot();
             if (prof_on) pc[7] += clock64() - tw;
+          } else {
+            wait_slot();
           }
           const uint32_t slot_addr = smem_base + kSmemA + ra.slot * kASlotBytes;
-          // two items at a time: their 16 tap loads (128-bit) are all requested before the first one is consumed,
-          // so a chunk costs two memory round trips instead of four
+          const float* fbase = (s >= 0) ? p.feat[s] + (ch - p.ch_off[s]) : nullptr;
+          // two items at a time: their (up to) 16 tap loads are requested before the first one is consumed
 #pragma unroll
           for (int ib = 0; ib < 4; ib += 2) {
+            const bool live0 = (s >= 0) && t_ok[ib], live1 = (s >= 0) && t_ok[ib + 1];
+            if (!live0 && !live1) {                               // the common case for the coarse scales
+              sts128(slot_addr + sw128_offset((wt >> 3) + 32 * ib, g), 0u, 0u, 0u, 0u);
+              sts128(slot_addr + sw128_offset((wt >> 3) + 32 * (ib + 1), g), 0u, 0u, 0u, 0u);
+              continue;
+            }
             float4 v[2][4][2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              const Taps& tp = taps[ib + u];
-              const bool live = (s >= 0) && tp.any;
-              const float* f = live ? p.feat[s] + (ch - p.ch_off[s]) : nullptr;
+              const uint32_t ok = (s >= 0) ? t_ok[ib + u] : 0u;
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                if (live && tp.off[t] >= 0) {
-                  v[u][t][0] = __ldg(reinterpret_cast<const float4*>(f + tp.off[t]));
-                  v[u][t][1] = __ldg(reinterpret_cast<const float4*>(f + tp.off[t]) + 1);
+                if ((ok >> t) & 1u) {
+                  const float4* src = reinterpret_cast<const float4*>(fbase + t_off[ib + u] + (t & 1) * dxo + (t >> 1) * dyo);
+                  v[u][t][0] = __ldg(src);
+                  v[u][t][1] = __ldg(src + 1);
                 } else {
                   v[u][t][0] = make_float4(0.f, 0.f, 0.f, 0.f);
                   v[u][t][1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -638,23 +673,25 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              const Taps& tp = taps[ib + u];
               const int row = (wt >> 3) + 32 * (ib + u);
+              const float w = t_w[ib + u], n = t_n[ib + u];
+              const float e = fsub(1.0f, w), so = fsub(1.0f, n);
+              const float tw4[4] = {fmul(so, e), fmul(so, w), fmul(n, e), fmul(n, w)};     // nw, ne, sw, se
               float acc[8];
               // out = ((v_nw*nw + v_ne*ne) + v_sw*sw) + v_se*se : separate roundings like ATen's CPU kernel
               // (an out-of-range tap contributes an exact +0)
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                const float w = tp.w[t];
+                const float wt_ = tw4[t];
                 const float4 a0 = v[u][t][0], a1 = v[u][t][1];
                 if (t == 0) {
-                  acc[0] = fmul(a0.x, w); acc[1] = fmul(a0.y, w); acc[2] = fmul(a0.z, w); acc[3] = fmul(a0.w, w);
-                  acc[4] = fmul(a1.x, w); acc[5] = fmul(a1.y, w); acc[6] = fmul(a1.z, w); acc[7] = fmul(a1.w, w);
+                  acc[0] = fmul(a0.x, wt_); acc[1] = fmul(a0.y, wt_); acc[2] = fmul(a0.z, wt_); acc[3] = fmul(a0.w, wt_);
+                  acc[4] = fmul(a1.x, wt_); acc[5] = fmul(a1.y, wt_); acc[6] = fmul(a1.z, wt_); acc[7] = fmul(a1.w, wt_);
                 } else {
-                  acc[0] = fadd(acc[0], fmul(a0.x, w)); acc[1] = fadd(acc[1], fmul(a0.y, w));
-                  acc[2] = fadd(acc[2], fmul(a0.z, w)); acc[3] = fadd(acc[3], fmul(a0.w, w));
-                  acc[4] = fadd(acc[4], fmul(a1.x, w)); acc[5] = fadd(acc[5], fmul(a1.y, w));
-                  acc[6] = fadd(acc[6], fmul(a1.z, w)); acc[7] = fadd(acc[7], fmul(a1.w, w));
+                  acc[0] = fadd(acc[0], fmul(a0.x, wt_)); acc[1] = fadd(acc[1], fmul(a0.y, wt_));
+                  acc[2] = fadd(acc[2], fmul(a0.z, wt_)); acc[3] = fadd(acc[3], fmul(a0.w, wt_));
+                  acc[4] = fadd(acc[4], fmul(a1.x, wt_)); acc[5] = fadd(acc[5], fmul(a1.y, wt_));
+                  acc[6] = fadd(acc[6], fmul(a1.z, wt_)); acc[7] = fadd(acc[7], fmul(a1.w, wt_));
                 }
               }
               sts128(slot_addr + sw128_offset(row, g), pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
@@ -666,7 +703,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       };
 
       // ---------------- epilogue: ACC (TMEM) -> [+bias (+h)] -> (scratch) -> relu -> fp16 A chunks -------------
-      //   bias_idx: which header vector; use_h: add the fp32 hidden state from scratch; write_h: store it back
+      //   bias_idx: which header vector; use_h: add the fp32 hidden state from scratch; write_h: store it back.
+      //   16-column groups; the TMEM load and the scratch loads of group g+1 are in flight while group g is processed.
       auto epilogue_to_act = [&](int bias_idx, bool use_h, bool write_h) {
         lap(1);
         mbar_wait(acc_full, acc_phase, a.error_flag);
@@ -674,33 +712,39 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         tc_fence_after();
         lap(2);
         const float4* b4 = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden);
+        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const int col0 = col_half * 256;
         // this warp writes A slots of chunks [4*col_half, 4*col_half+4); slots of an epilogue are ra.slot+0..7
-        // The fp32 hidden state comes from the L2-resident scratch: the 8 float4 of group g+1 are requested before
-        // group g is processed (software prefetch in registers), so one L2 latency is exposed per phase, not per group.
-        float4 hn[8];
+        uint32_t vn[16];
+        float4 hn[4];
+        tmem_ld16(trow + (uint32_t)col0, vn);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          hn[j] = use_h ? scratch4[(size_t)((col_half * 256 >> 2) + j) * kTileM + erow] : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int grp = 0; grp < 8; ++grp) {
-          const int col = col_half * 256 + grp * 32;
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, v);      // asynchronous until the wait
-          float4 hh[8];
+        for (int j = 0; j < 4; ++j)
+          hn[j] = use_h ? scratch4[(size_t)((col0 >> 2) + j) * kTileM + erow] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int grp = 0; grp < 16; ++grp) {
+          const int col = col0 + grp * 16;
+          tmem_ld_wait();
+          uint32_t v[16];
+          float4 hh[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) hh[j] = hn[j];
-          if (use_h && grp < 7) {
+          for (int j = 0; j < 16; ++j) v[j] = vn[j];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) hn[j] = scratch4[(size_t)(((col + 32) >> 2) + j) * kTileM + erow];
+          for (int j = 0; j < 4; ++j) hh[j] = hn[j];
+          if (grp < 15) {
+            tmem_ld16(trow + (uint32_t)(col + 16), vn);
+            if (use_h) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) hn[j] = scratch4[(size_t)(((col + 16) >> 2) + j) * kTileM + erow];
+            }
           }
           const int chunk = col >> 6;
           int slot = ra.slot + chunk;
           uint32_t ph = ra.phase;
           if (slot >= kASlots) { slot -= kASlots; ph ^= 1; }
-          if ((grp & 1) == 0) mbar_wait(a_empty(slot), ph ^ 1, a.error_flag);
+          if ((grp & 3) == 0) mbar_wait(a_empty(slot), ph ^ 1, a.error_flag);
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
-          tmem_ld_wait();
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {                        // 4 granules of 8 columns
+          for (int gq = 0; gq < 2; ++gq) {                        // 2 granules of 8 columns
             float h[8];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -797,7 +841,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       __syncwarp();
       lap(3);
     }
-    if (prof_on) {
+    if constexpr (PROF) if (prof_on) {
       unsigned long long* dst = a.prof + (size_t)blockIdx.x * 16;
       for (int i = 0; i < 4; ++i) dst[i] = (unsigned long long)pc[i];
       dst[4] = (unsigned long long)(clock64() - pt_start);
@@ -959,8 +1003,10 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
     return -2;                         // layers without an ACC-complete signal cannot be dumped
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc::point_mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
-    cudaFuncSetAttribute(tc::point_mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
+    cudaFuncSetAttribute(tc::point_mlp_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
+    cudaFuncSetAttribute(tc::point_mlp_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
+    cudaFuncSetAttribute(tc::point_mlp_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
+    cudaFuncSetAttribute(tc::point_mlp_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
     attr_set = true;
   }
   tc::KernelArgs a;
@@ -1004,7 +1050,7 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
     if (!max_pairs) {
       cfg.gridDim = dim3(num_sms() / 2 * 2);
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, tc::point_mlp_tc_kernel<2>, &cfg) != cudaSuccess || nc < 1) nc = num_sms() / 2;
+      if (cudaOccupancyMaxActiveClusters(&nc, tc::point_mlp_tc_kernel<2, false>, &cfg) != cudaSuccess || nc < 1) nc = num_sms() / 2;
       max_pairs = nc;
     }
     max_ctas = max_pairs * 2;
@@ -1013,8 +1059,13 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
   int grid = n_groups * cg < max_ctas ? n_groups * cg : max_ctas;
   if (grid > 256) grid = 256;
   cfg.gridDim = dim3(grid);
-  if (cg == 2) cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<2>, p, a);
-  else cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<1>, p, a);
+  if (prof_env) {
+    if (cg == 2) cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<2, true>, p, a);
+    else cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<1, true>, p, a);
+  } else {
+    if (cg == 2) cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<2, false>, p, a);
+    else cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<1, false>, p, a);
+  }
   if (prof_env) {            // diagnostics only: synchronises and prints mean per-CTA cycle counters
     static unsigned long long host[256 * 16];
     cudaStreamSynchronize(st);
