@@ -255,6 +255,12 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   // statements still keep their order relative to the fences / arrives that publish the tile)
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
+// {relu(lo), relu(hi)} -> packed fp16x2 in one instruction (the ReLU of the reference rides on the conversion)
+__device__ __forceinline__ uint32_t pack_relu_half2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -716,25 +722,28 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         const int col0 = col_half * 256;
         // this warp writes A slots of chunks [4*col_half, 4*col_half+4); slots of an epilogue are ra.slot+0..7
         uint32_t vn[16];
-        float4 hn[4];
+        float4 hn[4], bn[4];
         tmem_ld16(trow + (uint32_t)col0, vn);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 4; ++j) {
           hn[j] = use_h ? scratch4[(size_t)((col0 >> 2) + j) * kTileM + erow] : make_float4(0.f, 0.f, 0.f, 0.f);
+          bn[j] = __ldg(b4 + (col0 >> 2) + j);
+        }
         for (int grp = 0; grp < 16; ++grp) {
           const int col = col0 + grp * 16;
           tmem_ld_wait();
           uint32_t v[16];
-          float4 hh[4];
+          float4 hh[4], bb[4];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = vn[j];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) hh[j] = hn[j];
+          for (int j = 0; j < 4; ++j) { hh[j] = hn[j]; bb[j] = bn[j]; }
           if (grp < 15) {
             tmem_ld16(trow + (uint32_t)(col + 16), vn);
-            if (use_h) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) hn[j] = scratch4[(size_t)(((col + 16) >> 2) + j) * kTileM + erow];
+            for (int j = 0; j < 4; ++j) {
+              if (use_h) hn[j] = scratch4[(size_t)(((col + 16) >> 2) + j) * kTileM + erow];
+              bn[j] = __ldg(b4 + ((col + 16) >> 2) + j);       // 16 KB bias header: L1-resident broadcast load
             }
           }
           const int chunk = col >> 6;
@@ -745,23 +754,19 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
 #pragma unroll
           for (int gq = 0; gq < 2; ++gq) {                        // 2 granules of 8 columns
-            float h[8];
+            float4 r[2];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const int j = gq * 2 + half;
-              const float4 bb = __ldg(b4 + (col >> 2) + j);       // 16 KB bias header: L1-resident broadcast load
-              float4 r;
-              r.x = __uint_as_float(v[j * 4 + 0]) + bb.x + hh[j].x;
-              r.y = __uint_as_float(v[j * 4 + 1]) + bb.y + hh[j].y;
-              r.z = __uint_as_float(v[j * 4 + 2]) + bb.z + hh[j].z;
-              r.w = __uint_as_float(v[j * 4 + 3]) + bb.w + hh[j].w;
-              if (write_h) scratch4[(size_t)((col >> 2) + j) * kTileM + erow] = r;
-              h[half * 4 + 0] = fmaxf(r.x, 0.f); h[half * 4 + 1] = fmaxf(r.y, 0.f);
-              h[half * 4 + 2] = fmaxf(r.z, 0.f); h[half * 4 + 3] = fmaxf(r.w, 0.f);
+              r[half].x = __uint_as_float(v[j * 4 + 0]) + bb[j].x + hh[j].x;
+              r[half].y = __uint_as_float(v[j * 4 + 1]) + bb[j].y + hh[j].y;
+              r[half].z = __uint_as_float(v[j * 4 + 2]) + bb[j].z + hh[j].z;
+              r[half].w = __uint_as_float(v[j * 4 + 3]) + bb[j].w + hh[j].w;
+              if (write_h) scratch4[(size_t)((col >> 2) + j) * kTileM + erow] = r[half];
             }
             const int gcol = ((col & 63) >> 3) + gq;              // granule inside the 64-wide chunk
-            sts128(slot_addr + sw128_offset(erow, gcol), pack_half2(h[0], h[1]), pack_half2(h[2], h[3]),
-                   pack_half2(h[4], h[5]), pack_half2(h[6], h[7]));
+            sts128(slot_addr + sw128_offset(erow, gcol), pack_relu_half2(r[0].x, r[0].y), pack_relu_half2(r[0].z, r[0].w),
+                   pack_relu_half2(r[1].x, r[1].y), pack_relu_half2(r[1].z, r[1].w));
           }
         }
         // every TMEM read and smem write of this warp is done: release all 8 chunks (the next MMA overwrites ACC)
