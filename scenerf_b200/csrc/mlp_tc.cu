@@ -56,7 +56,7 @@ constexpr int kNumLayers = 11;
 constexpr int kSmemA = 0;
 constexpr int kSmemB = kSmemA + kASlots * kASlotBytes;                 // 131072
 constexpr int kSmemBar = kSmemB + kBSlots * kBSlotBytes;               // 229376
-constexpr int kNumBars = 2 * kASlots + 2 * kBSlots + 2;                // a_full/empty, b_full/empty, acc_full, meta
+constexpr int kNumBars = 2 * kASlots + 2 * kBSlots + 3;                // a_full/empty, b_full/empty, half_full[2], meta
 constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
 constexpr int kSmemMask = kSmemTmemPtr + 8;                            // 2 x uint64 active-chunk masks (double buffer)
 constexpr int kSmemSph = kSmemMask + 16;                               // int2 sx,sy per row: 1 KB
@@ -315,6 +315,61 @@ __device__ __forceinline__ uint64_t chunk_mask_for_scales(const DevParams& p, ui
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Tile program walker: the ONE definition of the order in which MMAs (and therefore weight images and A chunks) are
+// consumed.  The weight producer, the weight-full relay and the MMA issuer all walk it with their own visitor, so
+// they cannot disagree.
+//
+//   T0      lin_in (1 chunk) + lin_z0 (kz chunks), K-outer, both accumulator halves          -> EV_ALL
+//   fc_0 b  four S-groups of the 512x512 layer:  S1 (k0-3, half 0)  S2 (k0-3, half 1) -> EV_BANK0_FREE
+//                                                S3 (k4-7, half 0) -> EV_HALF0    S4 (k4-7, half 1) -> EV_BANK1_FREE, EV_HALF1
+//   fc_1 b  S1 S2 | lin_z(b+1) K-outer (accumulates into both halves) | S3 S4   (same events)
+//   lin_out 8 chunks, N = 16                                                                  -> EV_OUT
+// Accumulator half 0 of a layer is complete after S3 and half 1 after S4, so the epilogue of half 0 overlaps the
+// MMAs of S4 and the epilogue of half 1 overlaps S1 of the next layer (which only touches half 0 and A chunks 0-3).
+// ---------------------------------------------------------------------------------------------------------------
+enum OpKind { OP_KOUTER = 0, OP_SGROUP = 1, OP_OUT = 2 };
+enum EvKind { EV_ALL = 0, EV_BANK0_FREE = 1, EV_HALF0 = 2, EV_BANK1_FREE_HALF1 = 3, EV_OUT = 4, EV_PRE_S1 = 5, EV_PRE_S2 = 6 };
+
+template <class V>
+__device__ __forceinline__ void walk_tile(int kz, uint64_t mask, int last_layer, V& v) {
+  // T0
+  v.op(OP_KOUTER, 0, 0, 0, /*fresh*/ 1);
+  for (int c = 0; c < kz; ++c)
+    if ((mask >> c) & 1ull) v.op(OP_KOUTER, 1, c, 0, 0);
+  v.ev(EV_ALL);
+  if (last_layer == 1) return;
+  for (int b = 0; b < SRF_NUM_BLOCKS; ++b) {
+    for (int which = 0; which < 2; ++which) {               // 0: fc_0, 1: fc_1
+      const int l = 2 + 3 * b + which;
+      v.ev(EV_PRE_S1);
+      for (int k = 0; k < 4; ++k) v.op(OP_SGROUP, l, k, 0, k == 0);
+      v.ev(EV_PRE_S2);
+      for (int k = 0; k < 4; ++k) v.op(OP_SGROUP, l, k, 1, k == 0);
+      v.ev(EV_BANK0_FREE);
+      if (which == 1 && b < SRF_NUM_BLOCKS - 1) {
+        for (int c = 0; c < kz; ++c)
+          if ((mask >> c) & 1ull) v.op(OP_KOUTER, 4 + 3 * b, c, 0, 0);
+      }
+      for (int k = 4; k < 8; ++k) v.op(OP_SGROUP, l, k, 0, 0);
+      v.ev(EV_HALF0);
+      for (int k = 4; k < 8; ++k) v.op(OP_SGROUP, l, k, 1, 0);
+      v.ev(EV_BANK1_FREE_HALF1);
+      const int done_layer = (which == 0) ? l : ((b < SRF_NUM_BLOCKS - 1) ? 4 + 3 * b : 9);
+      if (last_layer == done_layer) return;
+    }
+  }
+  for (int k = 0; k < 8; ++k) v.op(OP_OUT, 10, k, 0, k == 0);
+  v.ev(EV_OUT);
+}
+
+// byte offset of the first image of chunk k of layer l inside the image region of the blob
+__device__ __forceinline__ size_t chunk_image_offset(int l, int k, int kz) {
+  size_t off = 0;
+  for (int i = 0; i < l; ++i) off += (size_t)layer_chunks(i, kz) * (kLayers[i].is_out ? kOutImgBytes : kQuarters * kBSlotBytes);
+  return off + (size_t)k * (kLayers[l].is_out ? kOutImgBytes : kQuarters * kBSlotBytes);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------------
 template <int CG, bool PROF>
@@ -330,8 +385,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
   auto a_empty = [&](int s) { return bar0 + 8u * (kASlots + s); };
   auto b_full = [&](int s) { return bar0 + 8u * (2 * kASlots + s); };
   auto b_empty = [&](int s) { return bar0 + 8u * (2 * kASlots + kBSlots + s); };
-  const uint32_t acc_full = bar0 + 8u * (2 * kASlots + 2 * kBSlots);
-  const uint32_t meta_full = acc_full + 8u;
+  auto half_full = [&](int h) { return bar0 + 8u * (2 * kASlots + 2 * kBSlots + h); };
+  const uint32_t meta_full = bar0 + 8u * (2 * kASlots + 2 * kBSlots + 2);
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
   volatile unsigned long long* mask_smem = reinterpret_cast<volatile unsigned long long*>(smem + kSmemMask);
   int2* sph_smem = reinterpret_cast<int2*>(smem + kSmemSph);
@@ -343,7 +398,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     for (int s = 0; s < kASlots; ++s) { mbar_init(a_full(s), kWorkerWarps * CG); mbar_init(a_empty(s), 1); }
     // B-full: the local producer's arrive.expect_tx (+ its bytes); on the leader of a pair also the peer's relay
     for (int s = 0; s < kBSlots; ++s) { mbar_init(b_full(s), (CG == 2 && leader) ? 2 : 1); mbar_init(b_empty(s), 1); }
-    mbar_init(acc_full, 1);
+    mbar_init(half_full(0), 1);
+    mbar_init(half_full(1), 1);
     mbar_init(meta_full, kWorkerWarps);
     mask_smem[0] = 0ull; mask_smem[1] = 0ull;
     fence_barrier_init();
@@ -362,162 +418,191 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
   const int kz = a.kz;
   const int last_layer = (a.debug_layer >= 0) ? a.debug_layer : (kNumLayers - 1);
   const unsigned char* images = a.wblob + kHeaderBytes;
-  constexpr int kImgPerChunk = kQuarters / CG;          // weight images this CTA stages per A chunk
   constexpr int kMmaN = kBRows * CG;                    // N of one MMA (128 rows from each CTA of the group)
+  constexpr int kHalves = kQuarters / CG;               // accumulator column groups of kMmaN: 2 halves (pairs) or 4 quarters
 
+  // ---- visitor pieces shared by producer and relay: which weight images does an op need from THIS CTA? ----------
+  //   OP_KOUTER: all column groups of chunk k  -> kHalves images (quarter i*CG + crank)
+  //   OP_SGROUP: one half h of chunk k.  CG=2: 1 image (quarter 2h + crank); CG=1: 2 images (quarters 2h, 2h+1)
+  //   OP_OUT:    the [16 x 64] image, 1/CG of it per CTA
   if (warp == 0) {
     // ===================================== weight producer =====================================================
-    // CG=2: CTA r stages rows [128 r, 128 r + 128) of every N=256 half, i.e. blob quarter q = 2*half + r.
     if (lane == 0) {
-      Ring rb;
+      struct Producer {
+        const unsigned char* images; uint32_t smem_base, bar0; int kz; uint32_t crank; int* err; Ring rb;
+        __device__ __forceinline__ uint32_t bfull(int s) const { return bar0 + 8u * (2 * kASlots + s); }
+        __device__ __forceinline__ uint32_t bempty(int s) const { return bar0 + 8u * (2 * kASlots + kBSlots + s); }
+        __device__ __forceinline__ void load(const unsigned char* src, uint32_t bytes) {
+          mbar_wait(bempty(rb.slot), rb.phase ^ 1, err);
+          mbar_arrive_expect_tx(bfull(rb.slot), bytes);
+          bulk_g2s(smem_base + kSmemB + rb.slot * kBSlotBytes, src, bytes, bfull(rb.slot));
+          rb.advance<kBSlots>();
+        }
+        __device__ __forceinline__ void op(int kind, int l, int k, int h, int) {
+          const unsigned char* base = images + chunk_image_offset(l, k, kz);
+          if (kind == OP_OUT) { load(base + (size_t)crank * (kOutImgBytes / CG), kOutImgBytes / CG); return; }
+          if (kind == OP_KOUTER) {
+            for (int i = 0; i < kHalves; ++i) load(base + (size_t)(i * CG + crank) * kBSlotBytes, kBSlotBytes);
+          } else {
+            if (CG == 2) load(base + (size_t)(2 * h + crank) * kBSlotBytes, kBSlotBytes);
+            else { load(base + (size_t)(2 * h) * kBSlotBytes, kBSlotBytes); load(base + (size_t)(2 * h + 1) * kBSlotBytes, kBSlotBytes); }
+          }
+        }
+        __device__ __forceinline__ void ev(int) {}
+      } prod{images, smem_base, bar0, kz, crank, a.error_flag, Ring()};
       uint32_t meta_phase = 0;
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
         uint64_t mask = ~0ull;
-        bool have_mask = !a.skip_zero;
-        size_t off = 0;
-        for (int l = 0; l <= last_layer; ++l) {
-          const int nc = layer_chunks(l, kz);
-          const bool is_out = kLayers[l].is_out;
-          if (kLayers[l].chunks_is_kz && !have_mask) {
-            mbar_wait(meta_full, meta_phase, a.error_flag);     // this tile group's chunk mask is published
-            mask = mask_smem[it & 1];
-            have_mask = true;
-          }
-          for (int c = 0; c < nc; ++c) {
-            const size_t chunk_bytes = is_out ? (size_t)kOutImgBytes : (size_t)kQuarters * kBSlotBytes;
-            if (chunk_active(l, c, mask)) {
-              const int nimg = is_out ? 1 : kImgPerChunk;
-              const uint32_t bytes = is_out ? kOutImgBytes / CG : kBSlotBytes;
-              for (int i = 0; i < nimg; ++i) {
-                const size_t src = is_out ? (size_t)crank * bytes : (size_t)(i * CG + crank) * kBSlotBytes;
-                mbar_wait(b_empty(rb.slot), rb.phase ^ 1, a.error_flag);
-                mbar_arrive_expect_tx(b_full(rb.slot), bytes);
-                bulk_g2s(smem_base + kSmemB + rb.slot * kBSlotBytes, images + off + src, bytes, b_full(rb.slot));
-                rb.advance<kBSlots>();
-              }
-            }
-            off += chunk_bytes;
-          }
+        if (a.skip_zero) {
+          mbar_wait(meta_full, meta_phase, a.error_flag);        // this tile group's chunk mask is published
+          meta_phase ^= 1;
+          mask = mask_smem[it & 1];
         }
-        if (a.skip_zero) meta_phase ^= 1;
+        walk_tile(kz, mask, last_layer, prod);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       // ===================================== MMA issuer (leader CTA) ===========================================
-      Ring ra, rb;
+      struct Issuer {
+        uint32_t smem_base, bar0, tmem_base; int* err; Ring rb; int fa; uint32_t full_par;
+        uint32_t idesc_main, idesc_out; long long wa, wb; bool prof_on;
+        __device__ __forceinline__ uint32_t afull(int s) const { return bar0 + 8u * s; }
+        __device__ __forceinline__ uint32_t aempty(int s) const { return bar0 + 8u * (kASlots + s); }
+        __device__ __forceinline__ uint32_t bfull(int s) const { return bar0 + 8u * (2 * kASlots + s); }
+        __device__ __forceinline__ uint32_t bempty(int s) const { return bar0 + 8u * (2 * kASlots + kBSlots + s); }
+        __device__ __forceinline__ uint32_t hfull(int h) const { return bar0 + 8u * (2 * kASlots + 2 * kBSlots + h); }
+        __device__ __forceinline__ void wait_a(int slot) {
+          const long long t0 = (PROF && prof_on) ? clock64() : 0;
+          mbar_wait_cluster(afull(slot), (full_par >> slot) & 1u, err);
+          if (PROF && prof_on) wa += clock64() - t0;
+          full_par ^= 1u << slot;
+        }
+        // weight image(s) of one accumulator column group: wait, 4 MMAs per image pair, release
+        __device__ __forceinline__ void mma_group(uint64_t adesc, int n_img, uint32_t dcol, uint32_t idesc, bool fresh) {
+          int bs[2];
+          for (int i = 0; i < n_img; ++i) {
+            const long long t0 = (PROF && prof_on) ? clock64() : 0;
+            mbar_wait_cluster(bfull(rb.slot), rb.phase, err);
+            if (PROF && prof_on) wb += clock64() - t0;
+            bs[i] = rb.slot;
+            rb.advance<kBSlots>();
+          }
+          tc_fence_after();
+          for (int i = 0; i < n_img; ++i) {
+            const uint64_t bdesc = make_desc_sw128(smem_base + kSmemB + bs[i] * kBSlotBytes);
+#pragma unroll
+            for (int k = 0; k < kChunkK / 16; ++k)     // +32 bytes per UMMA_K=16 fp16 inside the swizzle row: start address += 2
+              umma_f16<CG>(tmem_base + dcol + (uint32_t)(i * kMmaN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                           (fresh && k == 0) ? 0u : 1u);
+          }
+          for (int i = 0; i < n_img; ++i) umma_commit<CG>(bempty(bs[i]));
+        }
+        __device__ __forceinline__ void op(int kind, int l, int k, int h, int fresh) {
+          if (kind == OP_KOUTER) {
+            const int slot = fa;
+            fa = (fa + 1) & 3;
+            wait_a(slot);
+            tc_fence_after();
+            const uint64_t adesc = make_desc_sw128(smem_base + kSmemA + slot * kASlotBytes);
+            // CG=2: 2 images = 2 halves of 256 columns; CG=1: 4 images = 4 quarters of 128 columns
+            mma_group(adesc, 2, 0u, idesc_main, fresh != 0);
+            if (CG == 1) mma_group(adesc, 2, 2u * kMmaN, idesc_main, fresh != 0);
+            umma_commit<CG>(aempty(slot));
+          } else if (kind == OP_SGROUP) {
+            const uint64_t adesc = make_desc_sw128(smem_base + kSmemA + k * kASlotBytes);
+            mma_group(adesc, CG == 2 ? 1 : 2, (uint32_t)(h * 256), idesc_main, fresh != 0);
+          } else {
+            wait_a(k);
+            tc_fence_after();
+            const uint64_t adesc = make_desc_sw128(smem_base + kSmemA + k * kASlotBytes);
+            mma_group(adesc, 1, 0u, idesc_out, fresh != 0);
+            umma_commit<CG>(aempty(k));
+          }
+        }
+        __device__ __forceinline__ void ev(int e) {
+          switch (e) {
+            case EV_PRE_S1: for (int s = 0; s < 4; ++s) wait_a(s); tc_fence_after(); break;     // A chunks 0-3 ready, half 0 drained
+            case EV_PRE_S2: for (int s = 4; s < 8; ++s) wait_a(s); tc_fence_after(); break;     // A chunks 4-7 ready, half 1 drained
+            case EV_BANK0_FREE: for (int s = 0; s < 4; ++s) umma_commit<CG>(aempty(s)); break;
+            case EV_HALF0: umma_commit<CG>(hfull(0)); break;
+            case EV_BANK1_FREE_HALF1: for (int s = 4; s < 8; ++s) umma_commit<CG>(aempty(s)); umma_commit<CG>(hfull(1)); break;
+            case EV_ALL: umma_commit<CG>(hfull(0)); umma_commit<CG>(hfull(1)); break;
+            case EV_OUT: umma_commit<CG>(hfull(0)); break;
+          }
+        }
+      } iss{smem_base, bar0, tmem_base, a.error_flag, Ring(), 0, 0u,
+            make_idesc(kTileM * CG, kMmaN), make_idesc(kTileM * CG, kOutN), 0, 0, PROF && a.prof != nullptr};
       uint32_t meta_phase = 0;
-      long long wa = 0, wb = 0;                  // cycles the issuer waited for A chunks / weight images
-      const bool prof_on = PROF && a.prof != nullptr;
-      const uint32_t idesc_main = make_idesc(kTileM * CG, kMmaN);
-      const uint32_t idesc_out = make_idesc(kTileM * CG, kOutN);
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
         uint64_t mask = ~0ull;
-        bool have_mask = !a.skip_zero;
-        for (int l = 0; l <= last_layer; ++l) {
-          const int nc = layer_chunks(l, kz);
-          const bool is_out = kLayers[l].is_out;
-          if (kLayers[l].chunks_is_kz && !have_mask) {
-            mbar_wait(meta_full, meta_phase, a.error_flag);
-            mask = mask_smem[it & 1];
-            have_mask = true;
-          }
-          bool first = kLayers[l].fresh;           // the first executed chunk of a fresh layer overwrites ACC
-          for (int c = 0; c < nc; ++c) {
-            if (!chunk_active(l, c, mask)) continue;
-            long long t0 = prof_on ? clock64() : 0;
-            mbar_wait_cluster(a_full(ra.slot), ra.phase, a.error_flag);
-            if (prof_on) wa += clock64() - t0;
-            tc_fence_after();
-            const uint64_t adesc = make_desc_sw128(smem_base + kSmemA + ra.slot * kASlotBytes);
-            const int nh = is_out ? 1 : kImgPerChunk;
-            // all weight images of this chunk first, then the MMAs back to back, then the releases
-            int bslot[kQuarters];
-            for (int h = 0; h < nh; ++h) {
-              t0 = prof_on ? clock64() : 0;
-              mbar_wait_cluster(b_full(rb.slot), rb.phase, a.error_flag);
-              if (prof_on) wb += clock64() - t0;
-              bslot[h] = rb.slot;
-              rb.advance<kBSlots>();
-            }
-            tc_fence_after();
-            for (int h = 0; h < nh; ++h) {
-              const uint64_t bdesc = make_desc_sw128(smem_base + kSmemB + bslot[h] * kBSlotBytes);
-#pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) {
-                // +32 bytes per UMMA_K=16 fp16 inside the swizzle atom row: start address field += 2
-                umma_f16<CG>(tmem_base + (uint32_t)(h * kMmaN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
-                             is_out ? idesc_out : idesc_main, (first && k == 0) ? 0u : 1u);
-              }
-            }
-            for (int h = 0; h < nh; ++h) umma_commit<CG>(b_empty(bslot[h]));
-            first = false;
-            umma_commit<CG>(a_empty(ra.slot));
-            ra.advance<kASlots>();
-          }
-          if (kLayers[l].signal || l == last_layer) umma_commit<CG>(acc_full);
+        if (a.skip_zero) {
+          mbar_wait(meta_full, meta_phase, a.error_flag);
+          meta_phase ^= 1;
+          mask = mask_smem[it & 1];
         }
-        if (a.skip_zero) meta_phase ^= 1;
+        iss.fa = 0;
+        walk_tile(kz, mask, last_layer, iss);
       }
-      if (prof_on) { a.prof[(size_t)blockIdx.x * 16 + 8] = (unsigned long long)wa; a.prof[(size_t)blockIdx.x * 16 + 9] = (unsigned long long)wb; }
+      if (PROF && iss.prof_on) { a.prof[(size_t)blockIdx.x * 16 + 8] = (unsigned long long)iss.wa; a.prof[(size_t)blockIdx.x * 16 + 9] = (unsigned long long)iss.wb; }
     } else if (CG == 2 && lane == 0 && !leader) {
       // ===================================== weight-full relay (peer CTA) ======================================
       // walks the same image sequence as the producer; when a local image has landed, arrives on the leader's
       // barrier of the same slot (the leader's MMA reads this CTA's half of B through the pair datapath)
-      Ring rb;
+      struct Relay {
+        uint32_t bar0; int* err; Ring rb;
+        __device__ __forceinline__ void fwd() {
+          const uint32_t bar = bar0 + 8u * (2 * kASlots + rb.slot);
+          mbar_wait(bar, rb.phase, err);
+          mbar_arrive_remote(map_to_cta(bar, 0));
+          rb.advance<kBSlots>();
+        }
+        __device__ __forceinline__ void op(int kind, int, int, int, int) {
+          if (kind == OP_KOUTER) { for (int i = 0; i < kHalves; ++i) fwd(); } else fwd();
+        }
+        __device__ __forceinline__ void ev(int) {}
+      } rel{bar0, a.error_flag, Ring()};
       uint32_t meta_phase = 0;
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
         uint64_t mask = ~0ull;
-        bool have_mask = !a.skip_zero;
-        for (int l = 0; l <= last_layer; ++l) {
-          const int nc = layer_chunks(l, kz);
-          if (kLayers[l].chunks_is_kz && !have_mask) {
-            mbar_wait(meta_full, meta_phase, a.error_flag);
-            mask = mask_smem[it & 1];
-            have_mask = true;
-          }
-          for (int c = 0; c < nc; ++c) {
-            if (!chunk_active(l, c, mask)) continue;
-            const int nimg = kLayers[l].is_out ? 1 : kImgPerChunk;
-            for (int i = 0; i < nimg; ++i) {
-              mbar_wait(b_full(rb.slot), rb.phase, a.error_flag);
-              mbar_arrive_remote(map_to_cta(b_full(rb.slot), 0));
-              rb.advance<kBSlots>();
-            }
-          }
+        if (a.skip_zero) {
+          mbar_wait(meta_full, meta_phase, a.error_flag);
+          meta_phase ^= 1;
+          mask = mask_smem[it & 1];
         }
-        if (a.skip_zero) meta_phase ^= 1;
+        walk_tile(kz, mask, last_layer, rel);
       }
     }
   } else {
     // ===================================== workers =============================================================
     const int wt = threadIdx.x - 64;             // 0..255
     const int q4 = warp & 3;                     // TMEM lane quarter this warp may access
-    const int col_half = (warp >= 6) ? 1 : 0;    // warps (2,6),(3,7),(4,8),(5,9) share a quarter
+    const int sub = (warp >= 6) ? 1 : 0;         // warps (2,6),(3,7),(4,8),(5,9) share a quarter: 128 columns each per half
     const int erow = q4 * 32 + lane;             // epilogue row
     const float* bias = reinterpret_cast<const float*>(a.wblob);
     float4* scratch4 = reinterpret_cast<float4*>(a.scratch + (size_t)blockIdx.x * kTileM * kHidden);
-    Ring ra;
-    uint32_t acc_phase = 0;
+    int fa = 0;                                  // FIFO position in A bank 0 (slots 0..3): x / latent chunks
+    uint32_t fill_par = 0;                       // per-slot parity of the number of fills done by the workers
+    uint32_t half_par[2] = {0, 0};
+    uint32_t meta_phase = 0;
 
     // -- helpers -------------------------------------------------------------------------------------------
+    auto wait_slot_free = [&](int slot) { mbar_wait(a_empty(slot), ((fill_par >> slot) & 1u) ^ 1u, a.error_flag); };
     // A-full barriers live in the leader CTA: the MMA issuer there consumes the A tiles of both CTAs of a pair
     auto arrive_a_full = [&](int slot) {
       if constexpr (CG == 1) mbar_arrive(a_full(slot));
       else mbar_arrive_remote(map_to_cta(a_full(slot), 0));
     };
-    auto publish_chunk = [&]() {                 // all of this warp's writes to the current A slot are done
+    auto publish_slot = [&](int slot) {          // all of this warp's writes to the A slot are done
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) arrive_a_full(ra.slot);
-      ra.advance<kASlots>();
+      if (lane == 0) arrive_a_full(slot);
+      fill_par ^= 1u << slot;
     };
-    uint32_t meta_phase = 0;
-    auto wait_slot = [&]() { mbar_wait(a_empty(ra.slot), ra.phase ^ 1, a.error_flag); };
     // cycle accounting (one thread per CTA: first worker lane): 0 front-end, 1 gather passes, 2 waiting for ACC,
-    // 3 epilogue bodies, 4 whole kernel
+    // 3 epilogue E1 halves, 4 whole kernel, 5 E2 halves, 6 E3 halves, 7 blocked on A slots during gather
     const bool prof_on = PROF && (a.prof != nullptr) && (wt == 0);
-    long long pc[PROF ? 8 : 1] = {0};             // 5: E2-type, 6: E3, 7: time blocked in wait_slot during gather
+    long long pc[PROF ? 8 : 1] = {0};
     long long pt = prof_on ? clock64() : 0;
     const long long pt_start = pt;
     auto lap = [&](int idx) {
@@ -527,6 +612,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
       const int tile = grp_i * CG + (int)crank;
       const int row0 = tile * kTileM;
+      fa = 0;
       // ---------------- front-end: geometry of this tile's 128 points (threads 0..127, one point each) --------
       // With zero-chunk skipping in a CTA pair, threads 128..255 (idle here otherwise) run the same geometry for the
       // PEER's tile, so that both CTAs derive the identical union chunk mask locally (no cross-CTA exchange).
@@ -585,28 +671,31 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       }
       named_bar_sync(1, kWorkerThreads);          // sph_smem visible to all workers
 
-      // ---------------- L0: x chunk = [pe(39) | viewdir(3) | 0] as fp16 ---------------------------------------
-      wait_slot();
-      if (wt < kTileM) {
-        float xv[kChunkK];
+      // ---------------- L0: x chunk = [pe(39) | viewdir(3) | 0] as fp16 (FIFO slot) ---------------------------
+      {
+        const int slot = fa;
+        fa = (fa + 1) & 3;
+        wait_slot_free(slot);
+        if (wt < kTileM) {
+          float xv[kChunkK];
 #pragma unroll
-        for (int k = 0; k < kChunkK; ++k) xv[k] = 0.0f;
-        const int gi = row0 + wt;
-        if (gi < a.n) {
-          positional_encoding(px, py, pz, [&](int k, float v) { xv[k] = v; });
-          const float* vd = a.viewdir + (size_t)(gi / a.n_per) * 3;
-          xv[kDPE + 0] = vd[0]; xv[kDPE + 1] = vd[1]; xv[kDPE + 2] = vd[2];
+          for (int k = 0; k < kChunkK; ++k) xv[k] = 0.0f;
+          const int gi = row0 + wt;
+          if (gi < a.n) {
+            positional_encoding(px, py, pz, [&](int k, float v) { xv[k] = v; });
+            const float* vd = a.viewdir + (size_t)(gi / a.n_per) * 3;
+            xv[kDPE + 0] = vd[0]; xv[kDPE + 1] = vd[1]; xv[kDPE + 2] = vd[2];
+          }
+          const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            sts128(slot_addr + sw128_offset(wt, g), pack_half2(xv[8 * g + 0], xv[8 * g + 1]), pack_half2(xv[8 * g + 2], xv[8 * g + 3]),
+                   pack_half2(xv[8 * g + 4], xv[8 * g + 5]), pack_half2(xv[8 * g + 6], xv[8 * g + 7]));
         }
-        const uint32_t slot_addr = smem_base + kSmemA + ra.slot * kASlotBytes;
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          sts128(slot_addr + sw128_offset(wt, g), pack_half2(xv[8 * g + 0], xv[8 * g + 1]), pack_half2(xv[8 * g + 2], xv[8 * g + 3]),
-                 pack_half2(xv[8 * g + 4], xv[8 * g + 5]), pack_half2(xv[8 * g + 6], xv[8 * g + 7]));
+        publish_slot(slot);
       }
-      publish_chunk();
 
-      // ---------------- gather pass: produces the KZ latent chunks of one lin_z layer --------------------------
-      // thread -> 4 items per chunk: rows (wt/8) + 32*i, granule (8 channels = 16 B of fp16) g = wt % 8
+      // ---------------- gather pass: produces the latent chunks of one lin_z layer through the bank-0 FIFO ------
       // thread -> 4 items per chunk: rows (wt/8) + 32*i, granule (8 channels = 16 B of fp16) g = wt % 8.
       // Per row only (element offset of the north-west tap, x/y fractional weights, 4 validity bits) is kept in
       // registers; the 4 tap weights are re-derived (same products as scale_taps) when a chunk is gathered.
@@ -638,19 +727,20 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
               else if (tp.off[2] >= 0) o0 = tp.off[2] - dyo;
               else if (tp.off[3] >= 0) o0 = tp.off[3] - dxo - dyo;
               t_off[i] = o0;
-              // w[1] = so*w, w[0] = so*e ... keep (w, n): ne/nw = w/e split of the x axis, sw/nw = n/so of the y axis
               t_w[i] = tp.fx; t_n[i] = tp.fy;
             }
             cur_scale = s;
           }
+          const int slot = fa;
+          fa = (fa + 1) & 3;
           if constexpr (PROF) {
             const long long tw = prof_on ? clock64() : 0;
-            wait_slot();
+            wait_slot_free(slot);
             if (prof_on) pc[7] += clock64() - tw;
           } else {
-            wait_slot();
+            wait_slot_free(slot);
           }
-          const uint32_t slot_addr = smem_base + kSmemA + ra.slot * kASlotBytes;
+          const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
           const float* fbase = (s >= 0) ? p.feat[s] + (ch - p.ch_off[s]) : nullptr;
           // two items at a time: their (up to) 16 tap loads are requested before the first one is consumed
 #pragma unroll
@@ -704,23 +794,23 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
                      pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]));
             }
           }
-          publish_chunk();
+          publish_slot(slot);
         }
       };
 
-      // ---------------- epilogue: ACC (TMEM) -> [+bias (+h)] -> (scratch) -> relu -> fp16 A chunks -------------
-      //   bias_idx: which header vector; use_h: add the fp32 hidden state from scratch; write_h: store it back.
-      //   16-column groups; the TMEM load and the scratch loads of group g+1 are in flight while group g is processed.
-      auto epilogue_to_act = [&](int bias_idx, bool use_h, bool write_h) {
+      // ---------------- epilogue of one accumulator half: TMEM -> [+bias (+h)] -> (scratch) -> relu -> fp16 -------
+      //   part: 0 -> columns 0..255 -> A slots 0..3 ; 1 -> columns 256..511 -> A slots 4..7.  This warp: 128 columns
+      //   (2 A chunks).  bias_idx: header vector; use_h: add the fp32 hidden state from scratch; write_h: store it.
+      //   16-column groups; TMEM load, scratch and bias of group g+1 are in flight while group g is processed.
+      auto epilogue_half = [&](int part, int bias_idx, bool use_h, bool write_h) {
         lap(1);
-        mbar_wait(acc_full, acc_phase, a.error_flag);
-        acc_phase ^= 1;
+        mbar_wait(half_full(part), half_par[part], a.error_flag);
+        half_par[part] ^= 1;
         tc_fence_after();
         lap(2);
         const float4* b4 = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden);
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
-        const int col0 = col_half * 256;
-        // this warp writes A slots of chunks [4*col_half, 4*col_half+4); slots of an epilogue are ra.slot+0..7
+        const int col0 = part * 256 + sub * 128;
         uint32_t vn[16];
         float4 hn[4], bn[4];
         tmem_ld16(trow + (uint32_t)col0, vn);
@@ -729,7 +819,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           hn[j] = use_h ? scratch4[(size_t)((col0 >> 2) + j) * kTileM + erow] : make_float4(0.f, 0.f, 0.f, 0.f);
           bn[j] = __ldg(b4 + (col0 >> 2) + j);
         }
-        for (int grp = 0; grp < 16; ++grp) {
+        for (int grp = 0; grp < 8; ++grp) {
           const int col = col0 + grp * 16;
           tmem_ld_wait();
           uint32_t v[16];
@@ -738,7 +828,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           for (int j = 0; j < 16; ++j) v[j] = vn[j];
 #pragma unroll
           for (int j = 0; j < 4; ++j) { hh[j] = hn[j]; bb[j] = bn[j]; }
-          if (grp < 15) {
+          if (grp < 7) {
             tmem_ld16(trow + (uint32_t)(col + 16), vn);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -746,11 +836,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
               bn[j] = __ldg(b4 + ((col + 16) >> 2) + j);       // 16 KB bias header: L1-resident broadcast load
             }
           }
-          const int chunk = col >> 6;
-          int slot = ra.slot + chunk;
-          uint32_t ph = ra.phase;
-          if (slot >= kASlots) { slot -= kASlots; ph ^= 1; }
-          if ((grp & 3) == 0) mbar_wait(a_empty(slot), ph ^ 1, a.error_flag);
+          const int slot = col >> 6;                              // A chunk k lives in slot k
+          if ((grp & 3) == 0) wait_slot_free(slot);
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
 #pragma unroll
           for (int gq = 0; gq < 2; ++gq) {                        // 2 granules of 8 columns
@@ -769,27 +856,24 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
                    pack_relu_half2(r[1].x, r[1].y), pack_relu_half2(r[1].z, r[1].w));
           }
         }
-        // every TMEM read and smem write of this warp is done: release all 8 chunks (the next MMA overwrites ACC)
+        // every TMEM read and smem write of this warp for this half is done: publish the 4 A chunks of the half.
+        // (Every warp arrives on all 4, so "chunk k full" also means "the whole half has been drained from TMEM".)
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          for (int cidx = 0; cidx < kHiddenChunks; ++cidx) {
-            int slot = ra.slot + cidx;
-            if (slot >= kASlots) slot -= kASlots;
-            arrive_a_full(slot);
-          }
-        }
-        for (int cidx = 0; cidx < kHiddenChunks; ++cidx) ra.advance<kASlots>();
+        if (lane == 0)
+          for (int s = 4 * part; s < 4 * part + 4; ++s) arrive_a_full(s);
+        fill_par ^= 0xFu << (4 * part);
         lap(write_h ? 3 : (use_h ? 6 : 5));
       };
 
-      auto dump_acc = [&]() {                     // debug: raw accumulator of the current layer
-        mbar_wait(acc_full, acc_phase, a.error_flag);
-        acc_phase ^= 1;
+      auto dump_acc = [&](bool both_halves) {     // debug: raw accumulator of the current layer
+        mbar_wait(half_full(0), half_par[0], a.error_flag);
+        half_par[0] ^= 1;
+        if (both_halves) { mbar_wait(half_full(1), half_par[1], a.error_flag); half_par[1] ^= 1; }
         tc_fence_after();
         for (int grp = 0; grp < 8; ++grp) {
-          const int col = col_half * 256 + grp * 32;
+          const int col = sub * 256 + grp * 32;
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, v);
           tmem_ld_wait();
@@ -803,38 +887,35 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         named_bar_sync(1, kWorkerThreads);
       };
 
-      // ---------------- the tile program ---------------------------------------------------------------------
-      bool stop = false;
-      auto after_layer = [&](int l) {              // debug hook: true -> this tile ends here
-        if (a.debug_layer == l) { dump_acc(); stop = true; }
-        return stop;
-      };
+      // ---------------- the tile program (worker side; MMA side: walk_tile) -------------------------------------
       lap(0);
-      gather_pass();                                              // L1 lin_z0
-      if (after_layer(1)) continue;
-      for (int b = 0; b < SRF_NUM_BLOCKS && !stop; ++b) {
-        epilogue_to_act(/*bias*/ b, /*use_h*/ b > 0, /*write_h*/ true);        // E1 -> feeds fc_0
-        if (after_layer(2 + 3 * b)) break;
-        epilogue_to_act(/*bias*/ 3 + b, false, false);                          // E2 -> feeds fc_1
+      gather_pass();                                              // lin_z0
+      if (a.debug_layer == 1) { dump_acc(true); continue; }
+      bool stop = false;
+      for (int b = 0; b < SRF_NUM_BLOCKS; ++b) {
+        epilogue_half(0, b, b > 0, true);                         // E1a -> A chunks 0-3 of fc_0
+        epilogue_half(1, b, b > 0, true);                         // E1b
+        if (a.debug_layer == 2 + 3 * b) { dump_acc(true); stop = true; break; }
+        epilogue_half(0, 3 + b, false, false);                    // E2a -> A chunks 0-3 of fc_1 (overlaps fc_0 S4)
+        epilogue_half(1, 3 + b, false, false);                    // E2b (overlaps fc_1 S1)
         if (b < SRF_NUM_BLOCKS - 1) {
-          gather_pass();                                                        // lin_z(b+1)
-          if (after_layer(4 + 3 * b)) break;
-        } else {
-          if (after_layer(9)) break;
-        }
+          gather_pass();                                          // lin_z(b+1), consumed between fc_1 S2 and S3
+          if (a.debug_layer == 4 + 3 * b) { dump_acc(true); stop = true; break; }
+        } else if (a.debug_layer == 9) { dump_acc(true); stop = true; break; }
       }
       if (stop) continue;
-      epilogue_to_act(/*bias*/ 6, true, false);                                 // E3 -> feeds lin_out
-      if (after_layer(10)) continue;
+      epilogue_half(0, 6, true, false);                           // E3a -> A chunks of lin_out
+      epilogue_half(1, 6, true, false);                           // E3b
+      if (a.debug_layer == 10) { dump_acc(false); continue; }
       // ---------------- E4: out = ACC[:, :d_out] + b_out ------------------------------------------------------
       lap(1);
-      mbar_wait(acc_full, acc_phase, a.error_flag);
-      acc_phase ^= 1;
+      mbar_wait(half_full(0), half_par[0], a.error_flag);
+      half_par[0] ^= 1;
       tc_fence_after();
       lap(2);
-      if (col_half == 0) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16), v);   // 32 columns; only the first 16 are meaningful
+      if (sub == 0) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16), v);   // 16 columns
         tmem_ld_wait();
         const int gi = row0 + erow;
         if (gi < a.n) {
