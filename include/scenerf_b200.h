@@ -46,6 +46,10 @@ enum srf_precision {
 
 enum srf_dataset { SRF_KITTI = 0, SRF_BUNDLEFUSION = 1 };
 
+/* Storage of the packed feature pyramid.  FP32 is required by SRF_PREC_FP32.  FP16 halves the bytes of every bilinear
+ * tap (one 128-bit load per 8 channels) for the tensor-core mode, whose operands are rounded to fp16 anyway. */
+enum srf_pyramid_format { SRF_PYR_FP32 = 0, SRF_PYR_FP16 = 1 };
+
 /* The 22 tensors of one ResnetFC exactly as nn.Linear stores them: weight (out,in) row-major fp32, bias (out).
  * Reference: scenerf/models/resnetfc.py:66-131; state-dict names in comments. */
 typedef struct srf_mlp_weights {
@@ -67,8 +71,9 @@ typedef struct srf_mlp_weights {
 /* Feature pyramid of ONE input image, repacked channels-last ([H][W][C] fp32) by srf_pack_pyramid().
  * Reference input: x_rgb dict of CHW tensors, consumed at scenerf.py:522-525 / utils.py:232-247. */
 typedef struct srf_pyramid {
-  const float* hwc[SRF_NUM_SCALES];
+  const void* hwc[SRF_NUM_SCALES];   /* [H][W][C] of float (format 0) or IEEE half (format 1) */
   int C[SRF_NUM_SCALES], H[SRF_NUM_SCALES], W[SRF_NUM_SCALES];
+  int format;                        /* srf_pyramid_format */
 } srf_pyramid;
 
 /* Hyper-parameters the path reads from the module (scenerf.py:23-115) + per-call camera and pose. */
@@ -121,10 +126,10 @@ const char* srf_last_error(void);
 size_t srf_sizeof(int which);
 
 /* --- one-time packing ------------------------------------------------------------------------------------- */
-size_t srf_pyramid_bytes(const int* C, const int* H, const int* W);
-/* CHW fp32 (device) -> HWC fp32 into dst_dev; fills *out.  Replaces nothing in the reference: it is the layout
+size_t srf_pyramid_bytes(const int* C, const int* H, const int* W, int format);
+/* CHW fp32 (device) -> HWC fp32 / fp16 (srf_pyramid_format) into dst_dev; fills *out.  Replaces nothing in the reference: it is the layout
  * change that makes the 4-tap gather of utils.py:239-245 read contiguous channels. */
-int srf_pack_pyramid(const float* const* chw_dev, const int* C, const int* H, const int* W, void* dst_dev,
+int srf_pack_pyramid(const float* const* chw_dev, const int* C, const int* H, const int* W, int format, void* dst_dev,
                      size_t dst_bytes, srf_pyramid* out, void* stream);
 
 size_t srf_tc_weights_bytes(int d_out, int d_latent);

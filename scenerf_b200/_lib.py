@@ -15,6 +15,8 @@ NUM_BLOCKS = 3
 PREC_FP32 = 0
 PREC_FP16_TC = 1
 FLAG_SKIP_ZERO_CHUNKS = 1
+PYR_FP32 = 0
+PYR_FP16 = 1
 
 c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)
@@ -32,7 +34,7 @@ class MlpWeights(C.Structure):
 
 class Pyramid(C.Structure):
     _fields_ = [("hwc", C.c_void_p * NUM_SCALES), ("C", C.c_int * NUM_SCALES), ("H", C.c_int * NUM_SCALES),
-                ("W", C.c_int * NUM_SCALES)]
+                ("W", C.c_int * NUM_SCALES), ("format", C.c_int)]
 
 
 class Config(C.Structure):
@@ -62,9 +64,9 @@ SYMBOLS = {
     "srf_debug_watchdog_flag": (C.c_int, []),
     "srf_set_profiling": (None, [C.c_int]),
     "srf_last_mlp_ms": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
-    "srf_pyramid_bytes": (C.c_size_t, [C.POINTER(C.c_int)] * 3),
+    "srf_pyramid_bytes": (C.c_size_t, [C.POINTER(C.c_int)] * 3 + [C.c_int]),
     "srf_pack_pyramid": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
-                                   C.c_void_p, C.c_size_t, C.POINTER(Pyramid), C.c_void_p]),
+                                   C.c_int, C.c_void_p, C.c_size_t, C.POINTER(Pyramid), C.c_void_p]),
     "srf_tc_weights_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "srf_pack_weights_tc": (C.c_int, [C.POINTER(MlpWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
     "srf_render_workspace_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int]),

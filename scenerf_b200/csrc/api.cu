@@ -54,6 +54,8 @@ int validate(const srf_config* cfg, const srf_pyramid* pyr) {
   if (cfg->precision != SRF_PREC_FP32 && cfg->precision != SRF_PREC_FP16_TC)
     return fail(SRF_E_INVALID, "unknown precision %d", cfg->precision);
   if (pyr) {
+    if (cfg->precision == SRF_PREC_FP32 && pyr->format != SRF_PYR_FP32)
+      return fail(SRF_E_INVALID, "precision=FP32 needs a pyramid packed as SRF_PYR_FP32");
     for (int s = 0; s < SRF_NUM_SCALES; ++s) {
       if (!pyr->hwc[s] || pyr->C[s] < 1 || pyr->H[s] < 1 || pyr->W[s] < 1)
         return fail(SRF_E_INVALID, "pyramid scale %d is empty", s);
@@ -113,6 +115,7 @@ srf::DevParams make_params(const srf_config* cfg, const srf_pyramid* pyr) {
     for (int s = 0; s < SRF_NUM_SCALES; ++s) {
       const int scale = 1 << s;
       p.feat[s] = pyr->hwc[s];
+      p.feat_fp16 = pyr->format == SRF_PYR_FP16;
       p.C[s] = pyr->C[s]; p.H[s] = pyr->H[s]; p.W[s] = pyr->W[s];
       p.ch_off[s] = off;
       off += pyr->C[s];
@@ -225,25 +228,28 @@ size_t srf_sizeof(int which) {
   }
 }
 
-size_t srf_pyramid_bytes(const int* C, const int* H, const int* W) {
+size_t srf_pyramid_bytes(const int* C, const int* H, const int* W, int format) {
   size_t b = 0;
-  for (int s = 0; s < SRF_NUM_SCALES; ++s) b += align256((size_t)C[s] * H[s] * W[s] * sizeof(float));
+  const size_t esz = format == SRF_PYR_FP16 ? 2 : 4;
+  for (int s = 0; s < SRF_NUM_SCALES; ++s) b += align256((size_t)C[s] * H[s] * W[s] * esz);
   return b;
 }
 
-int srf_pack_pyramid(const float* const* chw_dev, const int* C, const int* H, const int* W, void* dst_dev,
+int srf_pack_pyramid(const float* const* chw_dev, const int* C, const int* H, const int* W, int format, void* dst_dev,
                      size_t dst_bytes, srf_pyramid* out, void* stream) {
   if (!chw_dev || !C || !H || !W || !dst_dev || !out) return fail(SRF_E_INVALID, "srf_pack_pyramid: NULL argument");
-  if (dst_bytes < srf_pyramid_bytes(C, H, W))
-    return fail(SRF_E_WORKSPACE, "srf_pack_pyramid: dst has %zu bytes, need %zu", dst_bytes, srf_pyramid_bytes(C, H, W));
+  if (format != SRF_PYR_FP32 && format != SRF_PYR_FP16) return fail(SRF_E_INVALID, "srf_pack_pyramid: format %d", format);
+  if (dst_bytes < srf_pyramid_bytes(C, H, W, format))
+    return fail(SRF_E_WORKSPACE, "srf_pack_pyramid: dst has %zu bytes, need %zu", dst_bytes, srf_pyramid_bytes(C, H, W, format));
+  const size_t esz = format == SRF_PYR_FP16 ? 2 : 4;
+  out->format = format;
   unsigned char* d = reinterpret_cast<unsigned char*>(dst_dev);
   for (int s = 0; s < SRF_NUM_SCALES; ++s) {
     if (!chw_dev[s] || C[s] < 1 || H[s] < 1 || W[s] < 1) return fail(SRF_E_INVALID, "srf_pack_pyramid: scale %d empty", s);
-    float* dst = reinterpret_cast<float*>(d);
-    srf::launch_chw_to_hwc(chw_dev[s], dst, C[s], H[s], W[s], (cudaStream_t)stream);
-    out->hwc[s] = dst;
+    srf::launch_chw_to_hwc(chw_dev[s], d, C[s], H[s], W[s], format == SRF_PYR_FP16, (cudaStream_t)stream);
+    out->hwc[s] = d;
     out->C[s] = C[s]; out->H[s] = H[s]; out->W[s] = W[s];
-    d += align256((size_t)C[s] * H[s] * W[s] * sizeof(float));
+    d += align256((size_t)C[s] * H[s] * W[s] * esz);
   }
   return check_cuda("srf_pack_pyramid");
 }

@@ -30,7 +30,8 @@ struct DevParams {
   float two_sig2;                     // float32(2*som_sigma**2)       (ray_som_kl.py:91)
   int U, G, P, S;
   // pyramid (channels-last)
-  const float* feat[kScales];
+  const void* feat[kScales];          // [H][W][C] float, or __half when feat_fp16
+  int feat_fp16;
   int C[kScales], H[kScales], W[kScales];
   int ch_off[kScales + 1];            // prefix sums of C
   float normW[kScales], normH[kScales];   // grid normaliser: (W,H) for scale 1, (W//s, H//s) otherwise (scenerf.py:522-525)

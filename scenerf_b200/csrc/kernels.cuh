@@ -15,7 +15,7 @@ void launch_composite_som(const DevParams& p, int R, const float* raw, const flo
                           cudaStream_t st);
 
 // pack.cu
-void launch_chw_to_hwc(const float* src, float* dst, int C, int H, int W, cudaStream_t st);
+void launch_chw_to_hwc(const float* src, void* dst, int C, int H, int W, bool fp16, cudaStream_t st);
 
 // mlp_simt.cu : float32 point MLP (gather + positional encoding + ResnetFC), n points in chunks.
 //   pts (n,3) infer-frame points; viewdir (n/n_per,3); raw_out (n,d_out).  Returns number of kernel launches.

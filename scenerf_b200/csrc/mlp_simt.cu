@@ -29,7 +29,7 @@ build_xin_kernel(const __grid_constant__ DevParams p, const float* __restrict__ 
 #pragma unroll
   for (int s = 0; s < kScales; ++s) {
     const Taps t = scale_taps(p, s, sx, sy);
-    const float* f = p.feat[s];
+    const float* f = reinterpret_cast<const float*>(p.feat[s]);
     float* dst = row + p.ch_off[s];
     for (int c = lane; c < p.C[s]; c += 32) {
       float acc = 0.0f;

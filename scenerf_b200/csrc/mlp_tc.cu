@@ -638,11 +638,12 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             for (int s = 0; s < 3; ++s) {
               const Taps tp = scale_taps(p, s, sx, sy);
               if (tp.any) {
-                const int bytes = p.C[s] * 4;
+                const int esz = p.feat_fp16 ? 2 : 4;
+                const int bytes = p.C[s] * esz;
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
                   if (tp.off[t] >= 0) {
-                    const char* base = reinterpret_cast<const char*>(p.feat[s] + tp.off[t]);
+                    const char* base = reinterpret_cast<const char*>(p.feat[s]) + (size_t)tp.off[t] * esz;
                     for (int b = 0; b < bytes; b += 128) prefetch_l2(base + b);
                     prefetch_l2(base + bytes - 4);
                   }
@@ -741,7 +742,50 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             wait_slot_free(slot);
           }
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
-          const float* fbase = (s >= 0) ? p.feat[s] + (ch - p.ch_off[s]) : nullptr;
+          // element index of this thread's first channel inside the scale's HWC map (features are float or half)
+          const char* fbytes = (s >= 0) ? reinterpret_cast<const char*>(p.feat[s]) : nullptr;
+          const int ch_in = (s >= 0) ? ch - p.ch_off[s] : 0;
+          const bool f16 = p.feat_fp16 != 0;
+          if (f16) {
+            // fp16 pyramid: a tap of 8 channels is ONE 128-bit load -> all 16 taps of the thread's 4 items are
+            // requested together (one memory round trip per chunk)
+            uint4 raw[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t ok = (s >= 0) ? t_ok[u] : 0u;
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                if ((ok >> t) & 1u) {
+                  const size_t eidx = (size_t)(ch_in + t_off[u] + (t & 1) * dxo + (t >> 1) * dyo);
+                  raw[u][t] = __ldg(reinterpret_cast<const uint4*>(fbytes + eidx * 2));
+                } else {
+                  raw[u][t] = make_uint4(0u, 0u, 0u, 0u);
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int row = (wt >> 3) + 32 * u;
+              if (!((s >= 0) && t_ok[u])) { sts128(slot_addr + sw128_offset(row, g), 0u, 0u, 0u, 0u); continue; }
+              const float w = t_w[u], n = t_n[u];
+              const float e = fsub(1.0f, w), so = fsub(1.0f, n);
+              const float tw4[4] = {fmul(so, e), fmul(so, w), fmul(n, e), fmul(n, w)};     // nw, ne, sw, se
+              float acc[8];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float wt_ = tw4[t];
+                const uint32_t rw[4] = {raw[u][t].x, raw[u][t].y, raw[u][t].z, raw[u][t].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[q]));
+                  if (t == 0) { acc[2 * q] = fmul(f.x, wt_); acc[2 * q + 1] = fmul(f.y, wt_); }
+                  else { acc[2 * q] = fadd(acc[2 * q], fmul(f.x, wt_)); acc[2 * q + 1] = fadd(acc[2 * q + 1], fmul(f.y, wt_)); }
+                }
+              }
+              sts128(slot_addr + sw128_offset(row, g), pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
+                     pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]));
+            }
+          } else {
           // two items at a time: their (up to) 16 tap loads are requested before the first one is consumed
 #pragma unroll
           for (int ib = 0; ib < 4; ib += 2) {
@@ -758,7 +802,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 if ((ok >> t) & 1u) {
-                  const float4* src = reinterpret_cast<const float4*>(fbase + t_off[ib + u] + (t & 1) * dxo + (t >> 1) * dyo);
+                  const size_t eidx = (size_t)(ch_in + t_off[ib + u] + (t & 1) * dxo + (t >> 1) * dyo);
+                  const float4* src = reinterpret_cast<const float4*>(fbytes + eidx * 4);
                   v[u][t][0] = __ldg(src);
                   v[u][t][1] = __ldg(src + 1);
                 } else {
@@ -793,6 +838,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
               sts128(slot_addr + sw128_offset(row, g), pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
                      pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]));
             }
+          }
           }
           publish_slot(slot);
         }

@@ -77,7 +77,7 @@ class B200Renderer:
     """
 
     def __init__(self, hp: dict, mlp_state, mlp_gaussian_state, device="cuda:0", precision: str = "fp16",
-                 rng: str = "philox", skip_zero_chunks: bool = False):
+                 rng: str = "philox", skip_zero_chunks: bool = False, pyramid_fp16: bool = True):
         if precision not in PRECISIONS:
             raise ValueError("precision must be one of %s" % list(PRECISIONS))
         if rng not in ("torch", "philox"):
@@ -90,6 +90,7 @@ class B200Renderer:
         self.precision = precision
         self.rng = rng
         self.skip_zero_chunks = skip_zero_chunks
+        self.pyramid_fp16 = pyramid_fp16      # fp16 mode: store the packed pyramid as fp16 (half the gather bytes)
         want_tc = precision == "fp16"
         self.mlp = _PackedMlp(mlp_state, 4, self.device, want_tc)
         self.mlp_gaussian = _PackedMlp(mlp_gaussian_state, 2, self.device, want_tc)
@@ -128,12 +129,13 @@ class B200Renderer:
         Cs = (C.c_int * 5)(*[t.shape[0] for t in src])
         Hs = (C.c_int * 5)(*[t.shape[1] for t in src])
         Ws = (C.c_int * 5)(*[t.shape[2] for t in src])
-        nbytes = self.lib.srf_pyramid_bytes(Cs, Hs, Ws)
+        fmt = _lib.PYR_FP16 if (self.precision == "fp16" and self.pyramid_fp16) else _lib.PYR_FP32
+        nbytes = self.lib.srf_pyramid_bytes(Cs, Hs, Ws, fmt)
         if self._pyr_buf is None or self._pyr_buf.numel() < nbytes:
             self._pyr_buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         ptrs = (C.c_void_p * 5)(*[t.data_ptr() for t in src])
         pyr = Pyramid()
-        _lib.check(self.lib.srf_pack_pyramid(ptrs, Cs, Hs, Ws, _ptr(self._pyr_buf), nbytes, C.byref(pyr),
+        _lib.check(self.lib.srf_pack_pyramid(ptrs, Cs, Hs, Ws, fmt, _ptr(self._pyr_buf), nbytes, C.byref(pyr),
                                              _stream_ptr(self.device)))
         self._pyr, self._pyr_key = pyr, key
         self._pyr_src = src          # keep sources alive until the async pack has certainly run

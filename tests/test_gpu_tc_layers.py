@@ -21,7 +21,9 @@ def emulate(cfg, params, pts, viewdir, x_rgb):
     p = pts.reshape(-1, 3).astype(np.float32)
     inv_K = np.linalg.inv(cfg.K).astype(np.float32)
     coords, _ = orc.sphere_coords_from_pixels(orc.cam_pts_2_pix(p, cfg.K), inv_K, cfg.angles(), cfg.sphere_W, cfg.sphere_H)
-    z = q16(orc.gather_latent(x_rgb, coords, cfg.sphere_W, cfg.sphere_H))
+    # tensor-core mode stores the packed pyramid as fp16 (features rounded once at pack time)
+    x16 = {k: np.asarray(v, dtype=np.float32).astype(np.float16).astype(np.float32) for k, v in x_rgb.items()}
+    z = q16(orc.gather_latent(x16, coords, cfg.sphere_W, cfg.sphere_H))
     x = q16(np.concatenate([orc.positional_encoding(p), np.repeat(viewdir, pts.shape[1], axis=0)], axis=1))
     W = lambda n: q16(params[n])
     b = lambda n: params[n].astype(np.float64)
