@@ -131,9 +131,16 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+// The 2 x 10.9 MB of weight images are re-read by every CTA for every tile while the feature pyramid streams through
+// L2 once per frame: ask L2 to keep the weights (evict_last) so that the stream sees L2-hit latency.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                : "memory");
 }
 
@@ -429,13 +436,13 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     // ===================================== weight producer =====================================================
     if (lane == 0) {
       struct Producer {
-        const unsigned char* images; uint32_t smem_base, bar0; int kz; uint32_t crank; int* err; Ring rb;
+        const unsigned char* images; uint32_t smem_base, bar0; int kz; uint32_t crank; int* err; Ring rb; uint64_t policy;
         __device__ __forceinline__ uint32_t bfull(int s) const { return bar0 + 8u * (2 * kASlots + s); }
         __device__ __forceinline__ uint32_t bempty(int s) const { return bar0 + 8u * (2 * kASlots + kBSlots + s); }
         __device__ __forceinline__ void load(const unsigned char* src, uint32_t bytes) {
           mbar_wait(bempty(rb.slot), rb.phase ^ 1, err);
           mbar_arrive_expect_tx(bfull(rb.slot), bytes);
-          bulk_g2s(smem_base + kSmemB + rb.slot * kBSlotBytes, src, bytes, bfull(rb.slot));
+          bulk_g2s(smem_base + kSmemB + rb.slot * kBSlotBytes, src, bytes, bfull(rb.slot), policy);
           rb.advance<kBSlots>();
         }
         __device__ __forceinline__ void op(int kind, int l, int k, int h, int) {
@@ -449,7 +456,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           }
         }
         __device__ __forceinline__ void ev(int) {}
-      } prod{images, smem_base, bar0, kz, crank, a.error_flag, Ring()};
+      } prod{images, smem_base, bar0, kz, crank, a.error_flag, Ring(), l2_policy_evict_last()};
       uint32_t meta_phase = 0;
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
         uint64_t mask = ~0ull;
@@ -632,23 +639,6 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           }
           if (own) {
             sph_smem[wt] = make_int2(sx, sy);
-            // warm L2 with the taps this row will gather from the (usually in-bounds) fine scales: the gather runs
-            // thousands of cycles later and then sees L2 instead of HBM latency
-#pragma unroll
-            for (int s = 0; s < 3; ++s) {
-              const Taps tp = scale_taps(p, s, sx, sy);
-              if (tp.any) {
-                const int esz = p.feat_fp16 ? 2 : 4;
-                const int bytes = p.C[s] * esz;
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                  if (tp.off[t] >= 0) {
-                    const char* base = reinterpret_cast<const char*>(p.feat[s]) + (size_t)tp.off[t] * esz;
-                    for (int b = 0; b < bytes; b += 128) prefetch_l2(base + b);
-                    prefetch_l2(base + bytes - 4);
-                  }
-              }
-            }
           }
           if (a.skip_zero) {
 #pragma unroll
@@ -677,21 +667,70 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         const int slot = fa;
         fa = (fa + 1) & 3;
         wait_slot_free(slot);
-        if (wt < kTileM) {
-          float xv[kChunkK];
-#pragma unroll
-          for (int k = 0; k < kChunkK; ++k) xv[k] = 0.0f;
-          const int gi = row0 + wt;
-          if (gi < a.n) {
-            positional_encoding(px, py, pz, [&](int k, float v) { xv[k] = v; });
-            const float* vd = a.viewdir + (size_t)(gi / a.n_per) * 3;
-            xv[kDPE + 0] = vd[0]; xv[kDPE + 1] = vd[1]; xv[kDPE + 2] = vd[2];
-          }
+        {
+          // two threads per row: thread wt < 128 writes granules 0-2 (x,y,z + the first 21 encodings), thread
+          // wt-128 writes granules 3-7 (the other 15 encodings, the view direction, zero padding) and issues the
+          // L2 prefetches of the row's gather taps
+          const bool first = wt < kTileM;
+          const int xrow = first ? wt : wt - kTileM;
+          const int gi = row0 + xrow;
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
+          float qx = px, qy = py, qz = pz;
+          if (!first) {
+            qx = qy = qz = 0.f;
+            if (gi < a.n) { qx = a.pts[(size_t)gi * 3 + 0]; qy = a.pts[(size_t)gi * 3 + 1]; qz = a.pts[(size_t)gi * 3 + 2]; }
+          }
+          const float c3[3] = {qx, qy, qz};
+          const float kPi = 3.14159274101257324f, kHalfPi = 1.57079637050628662f;
+          // value of x_in index idx (0..63) for this row: pe.py:32-43 order, then viewdir, then zeros
+          auto xval = [&](int idx, const float* vd) -> float {
+            if (gi >= a.n) return 0.0f;
+            if (idx < 3) return c3[idx];
+            if (idx < 3 + 36) {
+              const int j = idx - 3, fp = j / 3, cc = j % 3;        // fp = 2*k + phase
+              float arg = fmul(c3[cc], kPi * (float)(1 << (fp >> 1)));
+              if (fp & 1) arg = fadd(kHalfPi, arg);
+              return sinf(arg);
+            }
+            if (idx < kDX) return vd[idx - 39];
+            return 0.0f;
+          };
+          if (first) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            sts128(slot_addr + sw128_offset(wt, g), pack_half2(xv[8 * g + 0], xv[8 * g + 1]), pack_half2(xv[8 * g + 2], xv[8 * g + 3]),
-                   pack_half2(xv[8 * g + 4], xv[8 * g + 5]), pack_half2(xv[8 * g + 6], xv[8 * g + 7]));
+            for (int g = 0; g < 3; ++g)
+              sts128(slot_addr + sw128_offset(xrow, g), pack_half2(xval(8 * g + 0, nullptr), xval(8 * g + 1, nullptr)),
+                     pack_half2(xval(8 * g + 2, nullptr), xval(8 * g + 3, nullptr)), pack_half2(xval(8 * g + 4, nullptr), xval(8 * g + 5, nullptr)),
+                     pack_half2(xval(8 * g + 6, nullptr), xval(8 * g + 7, nullptr)));
+          } else {
+            float vd[3] = {0.f, 0.f, 0.f};
+            if (gi < a.n) {
+              const float* vp = a.viewdir + (size_t)(gi / a.n_per) * 3;
+              vd[0] = vp[0]; vd[1] = vp[1]; vd[2] = vp[2];
+            }
+#pragma unroll
+            for (int g = 3; g < 8; ++g)
+              sts128(slot_addr + sw128_offset(xrow, g), pack_half2(xval(8 * g + 0, vd), xval(8 * g + 1, vd)),
+                     pack_half2(xval(8 * g + 2, vd), xval(8 * g + 3, vd)), pack_half2(xval(8 * g + 4, vd), xval(8 * g + 5, vd)),
+                     pack_half2(xval(8 * g + 6, vd), xval(8 * g + 7, vd)));
+            // warm L2 with the taps this row will gather from the (usually in-bounds) fine scales: the gather runs
+            // thousands of cycles later and then sees L2 instead of HBM latency
+            const int2 sp = sph_smem[xrow];
+            const int esz = p.feat_fp16 ? 2 : 4;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const Taps tp = scale_taps(p, s, sp.x, sp.y);
+              if (tp.any) {
+                const int bytes = p.C[s] * esz;
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  if (tp.off[t] >= 0) {
+                    const char* base = reinterpret_cast<const char*>(p.feat[s]) + (size_t)tp.off[t] * esz;
+                    for (int b = 0; b < bytes; b += 128) prefetch_l2(base + b);
+                    prefetch_l2(base + bytes - 4);
+                  }
+              }
+            }
+          }
         }
         publish_slot(slot);
       }
@@ -746,7 +785,12 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           const char* fbytes = (s >= 0) ? reinterpret_cast<const char*>(p.feat[s]) : nullptr;
           const int ch_in = (s >= 0) ? ch - p.ch_off[s] : 0;
           const bool f16 = p.feat_fp16 != 0;
-          if (f16) {
+          const uint32_t any_live = (s >= 0) ? (t_ok[0] | t_ok[1] | t_ok[2] | t_ok[3]) : 0u;
+          if (!any_live) {
+            // nothing to gather for this thread's rows (the normal case for the coarse scales): zeros
+#pragma unroll
+            for (int u = 0; u < 4; ++u) sts128(slot_addr + sw128_offset((wt >> 3) + 32 * u, g), 0u, 0u, 0u, 0u);
+          } else if (f16) {
             // fp16 pyramid: a tap of 8 channels is ONE 128-bit load -> all 16 taps of the thread's 4 items are
             // requested together (one memory round trip per chunk)
             uint4 raw[4][4];
