@@ -901,31 +901,31 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         const float4* b4 = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden);
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const int col0 = part * 256 + sub * 128;
+        // Software pipeline (registers): the TMEM load of group g+1 and the scratch (fp32 hidden state, L2-resident)
+        // loads of groups g+1 and g+2 are in flight while group g is processed.
         uint32_t vn[16];
-        float4 hn[4], bn[4];
-        tmem_ld16(trow + (uint32_t)col0, vn);
+        float4 hx[4], hy[4];                       // hx: even groups, hy: odd groups
+        auto load_h = [&](float4 (&dst)[4], int c) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          hn[j] = use_h ? scratch4[(size_t)((col0 >> 2) + j) * kTileM + erow] : make_float4(0.f, 0.f, 0.f, 0.f);
-          bn[j] = __ldg(b4 + (col0 >> 2) + j);
-        }
-        for (int grp = 0; grp < 8; ++grp) {
+          for (int j = 0; j < 4; ++j)
+            dst[j] = use_h ? scratch4[(size_t)((c >> 2) + j) * kTileM + erow] : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        tmem_ld16(trow + (uint32_t)col0, vn);
+        load_h(hx, col0);
+        load_h(hy, col0 + 16);
+        auto process = [&](int grp, float4 (&hbuf)[4]) {
           const int col = col0 + grp * 16;
+          float4 bb[4], hh[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bb[j] = __ldg(b4 + (col >> 2) + j);   // 16 KB bias header: L1-resident broadcast
           tmem_ld_wait();
           uint32_t v[16];
-          float4 hh[4], bb[4];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = vn[j];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { hh[j] = hn[j]; bb[j] = bn[j]; }
-          if (grp < 7) {
-            tmem_ld16(trow + (uint32_t)(col + 16), vn);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (use_h) hn[j] = scratch4[(size_t)(((col + 16) >> 2) + j) * kTileM + erow];
-              bn[j] = __ldg(b4 + ((col + 16) >> 2) + j);       // 16 KB bias header: L1-resident broadcast load
-            }
-          }
+          for (int j = 0; j < 4; ++j) hh[j] = hbuf[j];
+          if (grp < 7) tmem_ld16(trow + (uint32_t)(col + 16), vn);
+          if (use_h && grp < 6) load_h(hbuf, col + 32);
           const int slot = col >> 6;                              // A chunk k lives in slot k
           if ((grp & 3) == 0) wait_slot_free(slot);
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
@@ -945,6 +945,10 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             sts128(slot_addr + sw128_offset(erow, gcol), pack_relu_half2(r[0].x, r[0].y), pack_relu_half2(r[0].z, r[0].w),
                    pack_relu_half2(r[1].x, r[1].y), pack_relu_half2(r[1].z, r[1].w));
           }
+        };
+        for (int grp = 0; grp < 8; grp += 2) {
+          process(grp, hx);
+          process(grp + 1, hy);
         }
         // every TMEM read and smem write of this warp for this half is done: publish the 4 A chunks of the half.
         // (Every warp arrives on all 4, so "chunk k full" also means "the whole half has been drained from TMEM".)
