@@ -114,3 +114,24 @@ def test_skip_zero_chunks_is_bit_identical():
                                                                   torch.from_numpy(g["viewdir"]), output_type="offset")
     torch.cuda.synchronize()
     assert torch.equal(a, b)
+
+
+def test_fp16_and_fp32_pyramid_storage_agree():
+    """tensor-core mode with the packed pyramid stored as fp16 (default) vs fp32: both within the fp16-mode tolerance
+    of the strict fp32 path; the storage format must not change a sphere-pixel decision."""
+    import torch
+    cfg, seed = PREDICT_CASES["predict_adversarial_kitti_full"]
+    g = load_golden("predict_adversarial_kitti_full")
+    x_rgb = torch_pyramid(cfg, seed)
+    K = torch.from_numpy(cfg.K)
+    pts, vd = torch.from_numpy(g["cam_pts"]), torch.from_numpy(g["viewdir"])
+    ref = make_renderer(cfg, "fp32").predict("mlp", pts, x_rgb, K, None, vd, output_type="offset").cpu().numpy()
+    outs = {}
+    for fp16_pyr in (True, False):
+        r = make_renderer(cfg, "fp16", pyramid_fp16=fp16_pyr)
+        raw, dbg = r.predict("mlp", pts, x_rgb, K, None, vd, output_type="offset", debug=True)
+        outs[fp16_pyr] = (raw.cpu().numpy(), dbg.cpu().numpy())
+    assert (outs[True][1] == outs[False][1]).all()
+    scale = max(1.0, np.abs(ref).max())
+    for k, (raw, _) in outs.items():
+        assert np.abs(raw - ref).max() <= 1e-2 * scale, k
