@@ -313,6 +313,40 @@ def main():
                 "kernel_ms": main_ms, "algorithmic_flop_per_launch": flop_launch, "peak_source": peak_src,
                 "whole_step_tflops": world * R * flop_per_ray(cfg) / (ms_per_step * 1e-3) / 1e12}
 
+    # ---- variants measured in the same run (not the headline): bit-identical zero-chunk skipping; strict fp32 mode --
+    variants = {}
+    try:
+        rs = B200Renderer(hp_from_cfg(cfg), to_t(pm), to_t(pg), device=dev, precision=args.precision, rng="philox",
+                          skip_zero_chunks=not bool(args.skip_zero_chunks))
+        for _ in range(2):
+            rs.render_rays_batch(K, T, x_rgb, sampled_pixels=pix_dev, outputs="minimal")
+        torch.cuda.synchronize()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(3):
+            rs.render_rays_batch(K, T, x_rgb, sampled_pixels=pix_dev, outputs="minimal")
+        v1.record()
+        torch.cuda.synchronize()
+        vms = v0.elapsed_time(v1) / 3
+        variants["skip_zero_chunks=%s" % (not bool(args.skip_zero_chunks))] = {
+            "ms_per_step": vms, "value": R / (vms * 1e-3), "unit": "rays/s",
+            "note": "lin_z K-chunks whose gathered features are zero for the whole tile pair are skipped; results bit-identical"}
+        del rs
+        if args.precision == "fp16":
+            n32 = min(R, 16384)
+            r32 = B200Renderer(hp_from_cfg(cfg), to_t(pm), to_t(pg), device=dev, precision="fp32", rng="philox")
+            r32.render_rays_batch(K, T, x_rgb, sampled_pixels=pix_dev[:n32], outputs="minimal")
+            torch.cuda.synchronize()
+            v0.record()
+            r32.render_rays_batch(K, T, x_rgb, sampled_pixels=pix_dev[:n32], outputs="minimal")
+            v1.record()
+            torch.cuda.synchronize()
+            variants["precision=fp32 (strict SIMT mode)"] = {"value": n32 / (v0.elapsed_time(v1) * 1e-3), "unit": "rays/s",
+                                                             "sample": "%d rays" % n32}
+            del r32
+    except Exception as e:          # variants are informational; never lose the headline line
+        variants["error"] = str(e).splitlines()[0]
+
     cpu = None
     parity = None
     if not args.no_cpu_baseline:
@@ -339,10 +373,10 @@ def main():
             "config": {"workload": desc, "rays_per_gpu": R, "samples_per_ray": cfg.S, "parallelism": "frame-per-GPU x%d" % world,
                        "precision": args.precision + (" operands, fp32 accumulate (tcgen05)" if args.precision == "fp16" else " SIMT"),
                        "skip_zero_chunks": bool(args.skip_zero_chunks), "outputs": "depth+color",
-                       "l2": "inputs larger than L2: 281 MB pyramid + 0.9 GB of per-step intermediates; no flush needed"},
+                       "l2": "inputs larger than L2: 140 MB fp16 pyramid + 21 MB weights + 1.9 GB of per-step intermediates (points, raw MLP output); no flush needed"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": R * 2 * 4, "d2h_bytes_per_step": R * 4 * 4},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "variants": variants}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

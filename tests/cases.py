@@ -11,6 +11,7 @@ RENDER_CASES = {
     "kitti_mini": (synth.config_A(name="kitti_mini", sphere_W=300, sphere_H=90, yaw_deg=10.0, tz=1.0), 31),
     "kitti_s128": (synth.config_B(name="kitti_s128", sphere_W=306, sphere_H=92), 32),
     "bf_mini": (synth.config_C(name="bf_mini", sphere_W=160, sphere_H=120, n_pts_uni=32), 33),
+    "bf_s96": (synth.config_C(name="bf_s96", sphere_W=160, sphere_H=120), 38),
     "kitti_identity": (synth.config_A(name="kitti_identity", sphere_W=300, sphere_H=90, yaw_deg=0.0, tz=0.0), 34),
 }
 

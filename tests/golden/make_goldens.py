@@ -237,6 +237,14 @@ def bf_mini():
 
 
 @case
+def bf_s96():
+    """BASELINE.json config C geometry: BundleFusion, U=64, G=4, P=8 -> S = 96 samples (not a power of two)."""
+    cfg = synth.config_C(name="bf_s96", sphere_W=160, sphere_H=120)
+    pix = synth.grid_pixels(cfg.img_W, cfg.img_H, stride=67)[:40]
+    return run_render_case(cfg, np.ascontiguousarray(pix), pyr_seed=38)
+
+
+@case
 def kitti_identity():
     """T = identity-ish (tz=0): all samples of a ray share one sphere pixel (SURVEY hard part 3c)."""
     cfg = synth.config_A(name="kitti_identity", sphere_W=300, sphere_H=90, yaw_deg=0.0, tz=0.0)
