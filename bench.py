@@ -25,6 +25,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (set before numpy loads BLAS)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(_k, None)
 
 import numpy as np  # noqa: E402
 

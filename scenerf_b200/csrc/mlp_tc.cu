@@ -29,9 +29,11 @@
 // leader CTA (rank 0) issues MMAs; the peer's workers arrive remotely on the leader's A-full barriers, the peer's
 // warp 1 relays its weight-full barriers to the leader, and the leader's tcgen05.commit multicasts the "empty" /
 // "accumulator complete" signals to both CTAs.  CG = 1 is the single-CTA variant (M = 128, N = 128).
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include "kernels.cuh"
 
 namespace srf {
@@ -82,6 +84,7 @@ struct KernelArgs {
   int d_out;
   int32_t* dbg_sphere;     // (n,2) or null
   int skip_zero;           // SRF_FLAG_SKIP_ZERO_CHUNKS
+  int use_tmap;            // CTA pairs: weight images by cp.async.bulk.tensor.cta_group::2 that signals the LEADER's barrier
   int debug_layer;         // -1, or: stop every tile after this layer's ACC is complete and dump it
   float* debug_acc;        // (n_tiles*128, 512)
   int* error_flag;         // set to non-zero by the watchdog
@@ -144,6 +147,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+// 2-D tiled TMA load whose mbarrier may live in the peer CTA of the pair (cta_group::2): both CTAs of a pair issue it
+// with their own shared-memory destination and the LEADER's barrier, so the MMA issuer waits on one barrier for both
+// halves of a weight tile (no relay hop).  c0 = element column, c1 = row of the [rows x 64] fp16 image tensor.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t mbar_cluster,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar_cluster), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -381,7 +395,8 @@ __device__ __forceinline__ size_t chunk_image_offset(int l, int k, int kz) {
 // ---------------------------------------------------------------------------------------------------------------
 template <int CG, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
-point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__ KernelArgs a) {
+point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__ KernelArgs a,
+                    const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_out) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   // SWIZZLE_128B tiles need 1024-byte alignment; the launch reserves 1 KB of slack for this round-up
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -404,7 +419,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     // A-full: every worker warp of every CTA of the group arrives (on the leader's barrier)
     for (int s = 0; s < kASlots; ++s) { mbar_init(a_full(s), kWorkerWarps * CG); mbar_init(a_empty(s), 1); }
     // B-full: the local producer's arrive.expect_tx (+ its bytes); on the leader of a pair also the peer's relay
-    for (int s = 0; s < kBSlots; ++s) { mbar_init(b_full(s), (CG == 2 && leader) ? 2 : 1); mbar_init(b_empty(s), 1); }
+    //         (with tensor-map loads both CTAs' bytes complete on the leader's barrier instead: one arrival)
+    for (int s = 0; s < kBSlots; ++s) { mbar_init(b_full(s), (CG == 2 && leader && !a.use_tmap) ? 2 : 1); mbar_init(b_empty(s), 1); }
     mbar_init(half_full(0), 1);
     mbar_init(half_full(1), 1);
     mbar_init(meta_full, kWorkerWarps);
@@ -437,6 +453,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     if (lane == 0) {
       struct Producer {
         const unsigned char* images; uint32_t smem_base, bar0; int kz; uint32_t crank; int* err; Ring rb; uint64_t policy;
+        const CUtensorMap* tmm; const CUtensorMap* tmo; bool use_tmap;
         __device__ __forceinline__ uint32_t bfull(int s) const { return bar0 + 8u * (2 * kASlots + s); }
         __device__ __forceinline__ uint32_t bempty(int s) const { return bar0 + 8u * (2 * kASlots + kBSlots + s); }
         __device__ __forceinline__ void load(const unsigned char* src, uint32_t bytes) {
@@ -445,7 +462,21 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           bulk_g2s(smem_base + kSmemB + rb.slot * kBSlotBytes, src, bytes, bfull(rb.slot), policy);
           rb.advance<kBSlots>();
         }
+        // pair + tensor map: the leader arms its barrier for the bytes of BOTH CTAs; each CTA loads its own half
+        __device__ __forceinline__ void load_t(const CUtensorMap* tm, int row, uint32_t bytes) {
+          mbar_wait(bempty(rb.slot), rb.phase ^ 1, err);
+          if (crank == 0) mbar_arrive_expect_tx(bfull(rb.slot), 2 * bytes);
+          tma_load_2d_pair(smem_base + kSmemB + rb.slot * kBSlotBytes, tm, 0, row, map_to_cta(bfull(rb.slot), 0), policy);
+          rb.advance<kBSlots>();
+        }
         __device__ __forceinline__ void op(int kind, int l, int k, int h, int) {
+          if (CG == 2 && use_tmap) {
+            if (kind == OP_OUT) { load_t(tmo, k * kOutN + (int)crank * (kOutN / 2), kOutImgBytes / 2); return; }
+            const int row0 = (int)(chunk_image_offset(l, k, kz) / 128);
+            if (kind == OP_KOUTER) { for (int i = 0; i < kHalves; ++i) load_t(tmm, row0 + (i * 2 + (int)crank) * kBRows, kBSlotBytes); }
+            else load_t(tmm, row0 + (2 * h + (int)crank) * kBRows, kBSlotBytes);
+            return;
+          }
           const unsigned char* base = images + chunk_image_offset(l, k, kz);
           if (kind == OP_OUT) { load(base + (size_t)crank * (kOutImgBytes / CG), kOutImgBytes / CG); return; }
           if (kind == OP_KOUTER) {
@@ -456,7 +487,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           }
         }
         __device__ __forceinline__ void ev(int) {}
-      } prod{images, smem_base, bar0, kz, crank, a.error_flag, Ring(), l2_policy_evict_last()};
+      } prod{images, smem_base, bar0, kz, crank, a.error_flag, Ring(), l2_policy_evict_last(), &tm_main, &tm_out, a.use_tmap != 0};
       uint32_t meta_phase = 0;
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
         uint64_t mask = ~0ull;
@@ -552,8 +583,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         walk_tile(kz, mask, last_layer, iss);
       }
       if (PROF && iss.prof_on) { a.prof[(size_t)blockIdx.x * 16 + 8] = (unsigned long long)iss.wa; a.prof[(size_t)blockIdx.x * 16 + 9] = (unsigned long long)iss.wb; }
-    } else if (CG == 2 && lane == 0 && !leader) {
-      // ===================================== weight-full relay (peer CTA) ======================================
+    } else if (CG == 2 && lane == 0 && !leader && !a.use_tmap) {
+      // ===================================== weight-full relay (peer CTA; only without tensor-map loads) =========
       // walks the same image sequence as the producer; when a local image has landed, arrives on the leader's
       // barrier of the same slot (the leader's MMA reads this CTA's half of B through the pair datapath)
       struct Relay {
@@ -1161,6 +1192,40 @@ static int num_sms() {
   return g_num_sms;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+// [rows x 64] fp16 row-major (128 B rows, already in shared-memory byte order), box = box_rows x 64
+static bool encode_image_map(CUtensorMap* tm, void* base, size_t rows, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || rows == 0) return false;
+  const cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool tc_use_tmap() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SRF_TC_TMAP"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v == 1;
+}
+
 static int tc_cta_group() {
   static int cg = -1;
   if (cg < 0) {
@@ -1239,12 +1304,25 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
   int grid = n_groups * cg < max_ctas ? n_groups * cg : max_ctas;
   if (grid > 256) grid = 256;
   cfg.gridDim = dim3(grid);
+  // tensor maps over the weight-image region of the blob (pair mode): [rows x 64] fp16, box = one stage image
+  CUtensorMap tm_main, tm_out;
+  memset(&tm_main, 0, sizeof(tm_main));
+  memset(&tm_out, 0, sizeof(tm_out));
+  a.use_tmap = 0;
+  if (cg == 2 && tc_use_tmap()) {
+    const size_t img_bytes = tc::images_bytes(a.kz);
+    unsigned char* img = const_cast<unsigned char*>(a.wblob) + tc::kHeaderBytes;
+    const size_t out_bytes = (size_t)tc::kHiddenChunks * tc::kOutImgBytes;
+    if (encode_image_map(&tm_main, img, (img_bytes - out_bytes) / 128, tc::kBRows) &&
+        encode_image_map(&tm_out, img + (img_bytes - out_bytes), out_bytes / 128, tc::kOutN / 2))
+      a.use_tmap = 1;
+  }
   if (prof_env) {
-    if (cg == 2) cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<2, true>, p, a);
-    else cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<1, true>, p, a);
+    if (cg == 2) cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<2, true>, p, a, tm_main, tm_out);
+    else cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<1, true>, p, a, tm_main, tm_out);
   } else {
-    if (cg == 2) cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<2, false>, p, a);
-    else cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<1, false>, p, a);
+    if (cg == 2) cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<2, false>, p, a, tm_main, tm_out);
+    else cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<1, false>, p, a, tm_main, tm_out);
   }
   if (prof_env) {            // diagnostics only: synchronises and prints mean per-CTA cycle counters
     static unsigned long long host[256 * 16];
