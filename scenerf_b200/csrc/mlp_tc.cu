@@ -58,7 +58,8 @@ constexpr int kNumLayers = 11;
 constexpr int kSmemA = 0;
 constexpr int kSmemB = kSmemA + kASlots * kASlotBytes;                 // 131072
 constexpr int kSmemBar = kSmemB + kBSlots * kBSlotBytes;               // 229376
-constexpr int kNumBars = 2 * kASlots + 2 * kBSlots + 3;                // a_full/empty, b_full/empty, half_full[2], meta
+constexpr int kZCache = 4;                        // latent chunks cached across the three lin_z passes (fine scales)
+constexpr int kNumBars = 2 * kASlots + 2 * kBSlots + 3 + 4;            // a_full/empty, b_full/empty, half_full[2], meta, zbar[4]
 constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
 constexpr int kSmemMask = kSmemTmemPtr + 8;                            // 2 x uint64 active-chunk masks (double buffer)
 constexpr int kSmemSph = kSmemMask + 16;                               // int2 sx,sy per row: 1 KB
@@ -87,6 +88,7 @@ struct KernelArgs {
   int use_tmap;            // CTA pairs: weight images by cp.async.bulk.tensor.cta_group::2 that signals the LEADER's barrier
   int debug_layer;         // -1, or: stop every tile after this layer's ACC is complete and dump it
   float* debug_acc;        // (n_tiles*128, 512)
+  unsigned char* zcache;   // gridDim.x * kZCache * 16 KB: gathered latent chunks 0..kZCache-1 of the current tile
   int* error_flag;         // set to non-zero by the watchdog
   unsigned long long* prof; // optional (SRF_TC_PROF=1): per-CTA cycle counters, 16 per CTA
 };
@@ -409,6 +411,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
   auto b_empty = [&](int s) { return bar0 + 8u * (2 * kASlots + kBSlots + s); };
   auto half_full = [&](int h) { return bar0 + 8u * (2 * kASlots + 2 * kBSlots + h); };
   const uint32_t meta_full = bar0 + 8u * (2 * kASlots + 2 * kBSlots + 2);
+  auto zbar = [&](int s) { return bar0 + 8u * (2 * kASlots + 2 * kBSlots + 3 + s); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
   volatile unsigned long long* mask_smem = reinterpret_cast<volatile unsigned long long*>(smem + kSmemMask);
   int2* sph_smem = reinterpret_cast<int2*>(smem + kSmemSph);
@@ -424,6 +427,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     mbar_init(half_full(0), 1);
     mbar_init(half_full(1), 1);
     mbar_init(meta_full, kWorkerWarps);
+    for (int s = 0; s < 4; ++s) mbar_init(zbar(s), 1);
     mask_smem[0] = 0ull; mask_smem[1] = 0ull;
     fence_barrier_init();
   }
@@ -623,6 +627,9 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     uint32_t fill_par = 0;                       // per-slot parity of the number of fills done by the workers
     uint32_t half_par[2] = {0, 0};
     uint32_t meta_phase = 0;
+    uint32_t zpar = 0;                           // parity per zbar slot
+    unsigned char* zc_base = a.zcache ? a.zcache + (size_t)blockIdx.x * kZCache * kASlotBytes : nullptr;
+    const uint64_t zpolicy = l2_policy_evict_last();
 
     // -- helpers -------------------------------------------------------------------------------------------
     auto wait_slot_free = [&](int slot) { mbar_wait(a_empty(slot), ((fill_par >> slot) & 1u) ^ 1u, a.error_flag); };
@@ -770,16 +777,49 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       // thread -> 4 items per chunk: rows (wt/8) + 32*i, granule (8 channels = 16 B of fp16) g = wt % 8.
       // Per row only (element offset of the north-west tap, x/y fractional weights, 4 validity bits) is kept in
       // registers; the 4 tap weights are re-derived (same products as scale_taps) when a chunk is gathered.
-      auto gather_pass = [&]() {
+      // The gathered chunks of the fine scales (chunks 0..kZCache-1: the ones that normally carry data) are identical
+      // for lin_z0/1/2: pass 0 also writes their fp16 tile images to an L2-resident per-CTA cache, passes 1 and 2
+      // bring them back with one cp.async.bulk each (all in flight together) instead of gathering again.
+      auto gather_pass = [&](int pass) {
         const int g = wt & 7;
+        int first_c = 0;
+        if (pass > 0 && zc_base) {
+          named_bar_sync(1, kWorkerThreads);      // pass-0 cache stores (+ their proxy fences) of every worker are done
+          int zs[kZCache];
+          int nz = 0;
+          for (int c = 0; c < kZCache && c < kz; ++c) {
+            if (!((mask >> c) & 1ull)) continue;
+            const int slot = fa;
+            fa = (fa + 1) & 3;
+            wait_slot_free(slot);
+            if (wt == 0) {
+              mbar_arrive_expect_tx(zbar(slot), kASlotBytes);
+              bulk_g2s(smem_base + kSmemA + slot * kASlotBytes, zc_base + (size_t)c * kASlotBytes, kASlotBytes, zbar(slot), zpolicy);
+            }
+            zs[nz++] = slot;
+          }
+          for (int i = 0; i < nz; ++i) {
+            mbar_wait(zbar(zs[i]), (zpar >> zs[i]) & 1u, a.error_flag);
+            zpar ^= 1u << zs[i];
+            publish_slot(zs[i]);
+          }
+          first_c = kZCache;
+        }
         int cur_scale = -1;
         int t_off[4];              // offset of tap 0 (may be "virtual" when tap 0 itself is out of range)
         uint32_t t_ok[4];          // bit t = tap t in range
         float t_w[4], t_n[4];      // fractional x / y weights (w, n of scale_taps)
         int dxo = 0, dyo = 0;      // element strides to the east / south tap
-        for (int c = 0; c < kz; ++c) {
+        for (int c = first_c; c < kz; ++c) {
           if (!((mask >> c) & 1ull)) continue;
           const int ch = c * kChunkK + g * 8;                     // first of this thread's 8 channels
+          // pass 0: mirror the tile image of the cached chunks to global (same swizzled byte order as the slot)
+          unsigned char* zc = (pass == 0 && zc_base && c < kZCache) ? zc_base + (size_t)c * kASlotBytes : nullptr;
+          auto emit = [&](int row, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t slot_addr_) {
+            const uint32_t off = sw128_offset(row, g);
+            sts128(slot_addr_ + off, w0, w1, w2, w3);
+            if (zc) *reinterpret_cast<uint4*>(zc + off) = make_uint4(w0, w1, w2, w3);
+          };
           int s = -1;
 #pragma unroll
           for (int i = 0; i < kScales; ++i)
@@ -820,7 +860,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           if (!any_live) {
             // nothing to gather for this thread's rows (the normal case for the coarse scales): zeros
 #pragma unroll
-            for (int u = 0; u < 4; ++u) sts128(slot_addr + sw128_offset((wt >> 3) + 32 * u, g), 0u, 0u, 0u, 0u);
+            for (int u = 0; u < 4; ++u) emit((wt >> 3) + 32 * u, 0u, 0u, 0u, 0u, slot_addr);
           } else if (f16) {
             // fp16 pyramid: a tap of 8 channels is ONE 128-bit load -> all 16 taps of the thread's 4 items are
             // requested together (one memory round trip per chunk)
@@ -841,7 +881,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int row = (wt >> 3) + 32 * u;
-              if (!((s >= 0) && t_ok[u])) { sts128(slot_addr + sw128_offset(row, g), 0u, 0u, 0u, 0u); continue; }
+              if (!((s >= 0) && t_ok[u])) { emit(row, 0u, 0u, 0u, 0u, slot_addr); continue; }
               const float w = t_w[u], n = t_n[u];
               const float e = fsub(1.0f, w), so = fsub(1.0f, n);
               const float tw4[4] = {fmul(so, e), fmul(so, w), fmul(n, e), fmul(n, w)};     // nw, ne, sw, se
@@ -857,8 +897,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
                   else { acc[2 * q] = fadd(acc[2 * q], fmul(f.x, wt_)); acc[2 * q + 1] = fadd(acc[2 * q + 1], fmul(f.y, wt_)); }
                 }
               }
-              sts128(slot_addr + sw128_offset(row, g), pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
-                     pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]));
+              emit(row, pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
+                     pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]), slot_addr);
             }
           } else {
           // two items at a time: their (up to) 16 tap loads are requested before the first one is consumed
@@ -866,8 +906,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           for (int ib = 0; ib < 4; ib += 2) {
             const bool live0 = (s >= 0) && t_ok[ib], live1 = (s >= 0) && t_ok[ib + 1];
             if (!live0 && !live1) {                               // the common case for the coarse scales
-              sts128(slot_addr + sw128_offset((wt >> 3) + 32 * ib, g), 0u, 0u, 0u, 0u);
-              sts128(slot_addr + sw128_offset((wt >> 3) + 32 * (ib + 1), g), 0u, 0u, 0u, 0u);
+              emit((wt >> 3) + 32 * ib, 0u, 0u, 0u, 0u, slot_addr);
+              emit((wt >> 3) + 32 * (ib + 1), 0u, 0u, 0u, 0u, slot_addr);
               continue;
             }
             float4 v[2][4][2];
@@ -910,13 +950,15 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
                   acc[6] = fadd(acc[6], fmul(a1.z, wt_)); acc[7] = fadd(acc[7], fmul(a1.w, wt_));
                 }
               }
-              sts128(slot_addr + sw128_offset(row, g), pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
-                     pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]));
+              emit(row, pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
+                     pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]), slot_addr);
             }
           }
           }
           publish_slot(slot);
         }
+        // the cache writes above are generic-proxy global stores; the later cp.async.bulk reads them via the async proxy
+        if (pass == 0 && zc_base) asm volatile("fence.proxy.async.global;" ::: "memory");
       };
 
       // ---------------- epilogue of one accumulator half: TMEM -> [+bias (+h)] -> (scratch) -> relu -> fp16 -------
@@ -1014,7 +1056,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
 
       // ---------------- the tile program (worker side; MMA side: walk_tile) -------------------------------------
       lap(0);
-      gather_pass();                                              // lin_z0
+      gather_pass(0);                                             // lin_z0
       if (a.debug_layer == 1) { dump_acc(true); continue; }
       bool stop = false;
       for (int b = 0; b < SRF_NUM_BLOCKS; ++b) {
@@ -1024,7 +1066,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         epilogue_half(0, 3 + b, false, false);                    // E2a -> A chunks 0-3 of fc_1 (overlaps fc_0 S4)
         epilogue_half(1, 3 + b, false, false);                    // E2b (overlaps fc_1 S1)
         if (b < SRF_NUM_BLOCKS - 1) {
-          gather_pass();                                          // lin_z(b+1), consumed between fc_1 S2 and S3
+          gather_pass(b + 1);                                     // lin_z(b+1), consumed between fc_1 S2 and S3
           if (a.debug_layer == 4 + 3 * b) { dump_acc(true); stop = true; break; }
         } else if (a.debug_layer == 9) { dump_acc(true); stop = true; break; }
       }
@@ -1237,7 +1279,8 @@ static int tc_cta_group() {
 
 size_t tc_workspace_bytes(int d_latent, int n_points) {
   (void)d_latent; (void)n_points;
-  return (size_t)256 * tc::kTileM * kHidden * sizeof(float) + 256;      // h scratch for up to 256 CTAs + error flag
+  // h scratch for up to 256 CTAs + latent-chunk cache + slack
+  return (size_t)256 * tc::kTileM * kHidden * sizeof(float) + (size_t)256 * tc::kZCache * tc::kASlotBytes + 256;
 }
 
 int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n,
@@ -1263,6 +1306,8 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
   a.raw_out = raw_out; a.d_out = w.d_out; a.dbg_sphere = dbg_sphere;
   a.skip_zero = (flags & SRF_FLAG_SKIP_ZERO_CHUNKS) ? 1 : 0;
   a.debug_layer = debug_layer; a.debug_acc = debug_acc;
+  a.zcache = reinterpret_cast<unsigned char*>(workspace) + (size_t)256 * tc::kTileM * kHidden * sizeof(float);
+  if (const char* e = getenv("SRF_TC_ZCACHE")) { if (atoi(e) == 0) a.zcache = nullptr; }
   // watchdog flag in mapped pinned host memory: still readable after a device-side trap killed the context
   if (!g_wd_host) {
     if (cudaHostAlloc(reinterpret_cast<void**>(&g_wd_host), sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
