@@ -50,7 +50,8 @@ int validate(const srf_config* cfg, const srf_pyramid* pyr) {
                 cfg->n_pts_per_gaussian);
   const int S = cfg->n_pts_uni + cfg->n_gaussians * cfg->n_pts_per_gaussian;
   if (S > 256) return fail(SRF_E_INVALID, "samples per ray S=%d exceeds 256", S);
-  if (cfg->sphere_W < 2 || cfg->sphere_H < 2) return fail(SRF_E_INVALID, "sphere grid %dx%d", cfg->sphere_W, cfg->sphere_H);
+  if (cfg->sphere_W < 2 || cfg->sphere_H < 2 || cfg->sphere_W > 16384 || cfg->sphere_H > 16384)
+    return fail(SRF_E_INVALID, "sphere grid %dx%d outside [2,16384]", cfg->sphere_W, cfg->sphere_H);
   if (cfg->precision != SRF_PREC_FP32 && cfg->precision != SRF_PREC_FP16_TC)
     return fail(SRF_E_INVALID, "unknown precision %d", cfg->precision);
   if (pyr) {

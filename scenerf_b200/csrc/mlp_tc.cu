@@ -62,8 +62,8 @@ constexpr int kZCache = 4;                        // latent chunks cached across
 constexpr int kNumBars = 2 * kASlots + 2 * kBSlots + 3 + 4;            // a_full/empty, b_full/empty, half_full[2], meta, zbar[4]
 constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
 constexpr int kSmemMask = kSmemTmemPtr + 8;                            // 2 x uint64 active-chunk masks (double buffer)
-constexpr int kSmemSph = kSmemMask + 16;                               // int2 sx,sy per row: 1 KB
-constexpr int kSmemTotal = kSmemSph + kTileM * 8;
+constexpr int kSmemSph = kSmemMask + 16;                               // 2 x short2 (sx,sy) per row: current + next tile
+constexpr int kSmemTotal = kSmemSph + 2 * kTileM * 4;
 static_assert(kSmemTotal + 1024 <= 232448, "shared memory budget");
 
 struct Layer { int chunks_is_kz, chunks, fresh, signal, is_out; };
@@ -414,7 +414,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
   auto zbar = [&](int s) { return bar0 + 8u * (2 * kASlots + 2 * kBSlots + 3 + s); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kSmemTmemPtr);
   volatile unsigned long long* mask_smem = reinterpret_cast<volatile unsigned long long*>(smem + kSmemMask);
-  int2* sph_smem = reinterpret_cast<int2*>(smem + kSmemSph);
+  short2* sph_smem = reinterpret_cast<short2*>(smem + kSmemSph);   // [2][128]
 
   const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader of the pair
   const bool leader = (crank == 0);
@@ -658,42 +658,44 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       const int tile = grp_i * CG + (int)crank;
       const int row0 = tile * kTileM;
       fa = 0;
-      // ---------------- front-end: geometry of this tile's 128 points (threads 0..127, one point each) --------
+      // ---------------- front-end: geometry of a tile's 128 points (threads 0..127, one point each) -----------
       // With zero-chunk skipping in a CTA pair, threads 128..255 (idle here otherwise) run the same geometry for the
       // PEER's tile, so that both CTAs derive the identical union chunk mask locally (no cross-CTA exchange).
-      float px = 0.f, py = 0.f, pz = 0.f;
-      uint32_t my_scales = 0;
-      {
+      // The geometry of tile it+1 is computed while tile `it` waits for its last fc_1 (double-buffered sph / mask).
+      auto geometry = [&](int grp, int it_) {
+        uint32_t my_scales = 0;
         const bool own = wt < kTileM;
         const int trow = own ? wt : wt - kTileM;
-        const int ttile = own ? tile : (grp_i * CG + (1 - (int)crank));
+        const int ttile = grp * CG + (own ? (int)crank : (1 - (int)crank));
         if (own || (CG == 2 && a.skip_zero)) {
           const int gi = ttile * kTileM + trow;
           int sx = kSphereInvalid, sy = kSphereInvalid;
           if (gi < a.n) {
-            px = a.pts[(size_t)gi * 3 + 0]; py = a.pts[(size_t)gi * 3 + 1]; pz = a.pts[(size_t)gi * 3 + 2];
-            point_to_sphere(p, px, py, pz, sx, sy);
+            point_to_sphere(p, a.pts[(size_t)gi * 3 + 0], a.pts[(size_t)gi * 3 + 1], a.pts[(size_t)gi * 3 + 2], sx, sy);
             if (own && a.dbg_sphere) { a.dbg_sphere[(size_t)gi * 2 + 0] = sx; a.dbg_sphere[(size_t)gi * 2 + 1] = sy; }
           }
-          if (own) {
-            sph_smem[wt] = make_int2(sx, sy);
-          }
+          // 16-bit storage: anything beyond +-32767 can only address zero padding (sphere grids are <= 16384 wide)
+          if (own) sph_smem[(it_ & 1) * kTileM + wt] = make_short2((short)max(min(sx, 32767), -32768), (short)max(min(sy, 32767), -32768));
           if (a.skip_zero) {
 #pragma unroll
             for (int s = 0; s < kScales; ++s) my_scales |= scale_taps(p, s, sx, sy).any ? (1u << s) : 0u;
           }
         }
-      }
+        if (a.skip_zero) {
+          // chunk mask of that tile group: its buffer was zeroed at the top of the previous tile
+          const uint32_t wbits = __reduce_or_sync(0xffffffffu, my_scales);
+          if (lane == 0) {
+            const unsigned long long bits = chunk_mask_for_scales(p, wbits, kz);
+            if (bits) atomicOr((unsigned long long*)&mask_smem[it_ & 1], bits);
+            mbar_arrive(meta_full);
+          }
+        }
+      };
+      if (it == 0 || a.debug_layer >= 0) geometry(grp_i, it);
+      const short2* sph_cur = sph_smem + (it & 1) * kTileM;
       uint64_t mask = ~0ull;
       if (a.skip_zero) {
-        // chunk mask of this tile group: buffer (it&1) was zeroed one tile ago
-        const uint32_t wbits = __reduce_or_sync(0xffffffffu, my_scales);
-        if (wt == 0) mask_smem[(it + 1) & 1] = 0ull;
-        if (lane == 0) {
-          const unsigned long long bits = chunk_mask_for_scales(p, wbits, kz);
-          if (bits) atomicOr((unsigned long long*)&mask_smem[it & 1], bits);
-          mbar_arrive(meta_full);
-        }
+        if (wt == 0) mask_smem[(it + 1) & 1] = 0ull;          // buffer of the NEXT tile group (filled later in this tile)
         mbar_wait(meta_full, meta_phase, a.error_flag);
         meta_phase ^= 1;
         mask = mask_smem[it & 1];
@@ -713,11 +715,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           const int xrow = first ? wt : wt - kTileM;
           const int gi = row0 + xrow;
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
-          float qx = px, qy = py, qz = pz;
-          if (!first) {
-            qx = qy = qz = 0.f;
-            if (gi < a.n) { qx = a.pts[(size_t)gi * 3 + 0]; qy = a.pts[(size_t)gi * 3 + 1]; qz = a.pts[(size_t)gi * 3 + 2]; }
-          }
+          float qx = 0.f, qy = 0.f, qz = 0.f;
+          if (gi < a.n) { qx = a.pts[(size_t)gi * 3 + 0]; qy = a.pts[(size_t)gi * 3 + 1]; qz = a.pts[(size_t)gi * 3 + 2]; }
           const float c3[3] = {qx, qy, qz};
           const float kPi = 3.14159274101257324f, kHalfPi = 1.57079637050628662f;
           // value of x_in index idx (0..63) for this row: pe.py:32-43 order, then viewdir, then zeros
@@ -752,7 +751,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
                      pack_half2(xval(8 * g + 6, vd), xval(8 * g + 7, vd)));
             // warm L2 with the taps this row will gather from the (usually in-bounds) fine scales: the gather runs
             // thousands of cycles later and then sees L2 instead of HBM latency
-            const int2 sp = sph_smem[xrow];
+            const short2 sp16 = sph_cur[xrow];
+            const int2 sp = make_int2(sp16.x, sp16.y);
             const int esz = p.feat_fp16 ? 2 : 4;
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
@@ -828,7 +828,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             dxo = p.C[s]; dyo = p.W[s] * p.C[s];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int2 sp = sph_smem[(wt >> 3) + 32 * i];
+              const short2 sp16 = sph_cur[(wt >> 3) + 32 * i];
+              const int2 sp = make_int2(sp16.x, sp16.y);
               const Taps tp = scale_taps(p, s, sp.x, sp.y);
               t_ok[i] = (tp.off[0] >= 0 ? 1u : 0u) | (tp.off[1] >= 0 ? 2u : 0u) | (tp.off[2] >= 0 ? 4u : 0u) | (tp.off[3] >= 0 ? 8u : 0u);
               // off[t] = off0 + (t&1)*dxo + (t>>1)*dyo for in-range taps -> recover off0 from any valid tap
@@ -1068,7 +1069,11 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         if (b < SRF_NUM_BLOCKS - 1) {
           gather_pass(b + 1);                                     // lin_z(b+1), consumed between fc_1 S2 and S3
           if (a.debug_layer == 4 + 3 * b) { dump_acc(true); stop = true; break; }
-        } else if (a.debug_layer == 9) { dump_acc(true); stop = true; break; }
+        } else {
+          // last block: nothing to gather while fc_1 runs -> prepare the next tile's geometry / chunk mask now
+          if (a.debug_layer < 0 && grp_i + n_cgroups < n_groups) geometry(grp_i + n_cgroups, it + 1);
+          if (a.debug_layer == 9) { dump_acc(true); stop = true; break; }
+        }
       }
       if (stop) continue;
       epilogue_half(0, 6, true, false);                           // E3a -> A chunks of lin_out
