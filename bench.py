@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--skip-zero-chunks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rays", type=int, default=0, help="diagnostics: use only the first N rays of the workload")
+    ap.add_argument("--no-variants", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -320,6 +321,8 @@ def main():
     # ---- variants measured in the same run (not the headline): bit-identical zero-chunk skipping; strict fp32 mode --
     variants = {}
     try:
+        if args.no_variants:
+            raise RuntimeError("variants disabled (--no-variants)")
         rs = B200Renderer(hp_from_cfg(cfg), to_t(pm), to_t(pg), device=dev, precision=args.precision, rng="philox",
                           skip_zero_chunks=not bool(args.skip_zero_chunks))
         for _ in range(2):

@@ -85,6 +85,7 @@ struct KernelArgs {
   int d_out;
   int32_t* dbg_sphere;     // (n,2) or null
   int skip_zero;           // SRF_FLAG_SKIP_ZERO_CHUNKS
+  int hidden_fp16;         // SRF_FLAG_HIDDEN_FP16: the hidden state travels between blocks as fp16 (scratch bytes halved)
   int use_tmap;            // CTA pairs: weight images by cp.async.bulk.tensor.cta_group::2 that signals the LEADER's barrier
   int debug_layer;         // -1, or: stop every tile after this layer's ACC is complete and dump it
   float* debug_acc;        // (n_tiles*128, 512)
@@ -395,7 +396,7 @@ __device__ __forceinline__ size_t chunk_image_offset(int l, int k, int kz) {
 // ---------------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int CG, bool PROF>
+template <int CG, bool PROF, bool H16>
 __global__ void __launch_bounds__(kThreads, 1)
 point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__ KernelArgs a,
                     const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_out) {
@@ -978,11 +979,23 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         // Software pipeline (registers): the TMEM load of group g+1 and the scratch (fp32 hidden state, L2-resident)
         // loads of groups g+1 and g+2 are in flight while group g is processed.
         uint32_t vn[16];
-        float4 hx[4], hy[4];                       // hx: even groups, hy: odd groups
+        float4 hx[4], hy[4];                       // hx: even groups, hy: odd groups (fp16 mode: raw halves in [0],[1])
+        constexpr bool h16 = H16;                  // hidden state carried as fp16 (SRF_FLAG_HIDDEN_FP16)
+        uint4* scratch8 = reinterpret_cast<uint4*>(scratch4);      // fp16 mode: 8 halves per uint4, [col/8][row]
         auto load_h = [&](float4 (&dst)[4], int c) {
+          if (!use_h) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = use_h ? scratch4[(size_t)((c >> 2) + j) * kTileM + erow] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else if (h16) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint4 raw = scratch8[(size_t)((c >> 3) + j) * kTileM + erow];
+              dst[j] = make_float4(__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = scratch4[(size_t)((c >> 2) + j) * kTileM + erow];
+          }
         };
         tmem_ld16(trow + (uint32_t)col0, vn);
         load_h(hx, col0);
@@ -996,8 +1009,22 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           uint32_t v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = vn[j];
+          if (use_h && h16) {
+            // unpack 16 halves (2 x uint4) -> 4 float4
 #pragma unroll
-          for (int j = 0; j < 4; ++j) hh[j] = hbuf[j];
+            for (int j = 0; j < 2; ++j) {
+              const uint32_t rw[4] = {__float_as_uint(hbuf[j].x), __float_as_uint(hbuf[j].y), __float_as_uint(hbuf[j].z), __float_as_uint(hbuf[j].w)};
+              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&rw[0]));
+              const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&rw[1]));
+              const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&rw[2]));
+              const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&rw[3]));
+              hh[2 * j] = make_float4(f0.x, f0.y, f1.x, f1.y);
+              hh[2 * j + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hh[j] = hbuf[j];
+          }
           if (grp < 7) tmem_ld16(trow + (uint32_t)(col + 16), vn);
           if (use_h && grp < 6) load_h(hbuf, col + 32);
           const int slot = col >> 6;                              // A chunk k lives in slot k
@@ -1013,8 +1040,11 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
               r[half].y = __uint_as_float(v[j * 4 + 1]) + bb[j].y + hh[j].y;
               r[half].z = __uint_as_float(v[j * 4 + 2]) + bb[j].z + hh[j].z;
               r[half].w = __uint_as_float(v[j * 4 + 3]) + bb[j].w + hh[j].w;
-              if (write_h) scratch4[(size_t)((col >> 2) + j) * kTileM + erow] = r[half];
+              if (write_h && !h16) scratch4[(size_t)((col >> 2) + j) * kTileM + erow] = r[half];
             }
+            if (write_h && h16)
+              scratch8[(size_t)((col >> 3) + gq) * kTileM + erow] =
+                  make_uint4(pack_half2(r[0].x, r[0].y), pack_half2(r[0].z, r[0].w), pack_half2(r[1].x, r[1].y), pack_half2(r[1].z, r[1].w));
             const int gcol = ((col & 63) >> 3) + gq;              // granule inside the 64-wide chunk
             sts128(slot_addr + sw128_offset(erow, gcol), pack_relu_half2(r[0].x, r[0].y), pack_relu_half2(r[0].z, r[0].w),
                    pack_relu_half2(r[1].x, r[1].y), pack_relu_half2(r[1].z, r[1].w));
@@ -1273,6 +1303,16 @@ static bool tc_use_tmap() {
   return v == 1;
 }
 
+using TcKernelFn = void (*)(const DevParams, const tc::KernelArgs, const CUtensorMap, const CUtensorMap);
+static TcKernelFn tc_kernel(int cg, bool prof, bool h16) {
+  static const TcKernelFn table[8] = {
+      tc::point_mlp_tc_kernel<1, false, false>, tc::point_mlp_tc_kernel<2, false, false>,
+      tc::point_mlp_tc_kernel<1, true, false>,  tc::point_mlp_tc_kernel<2, true, false>,
+      tc::point_mlp_tc_kernel<1, false, true>,  tc::point_mlp_tc_kernel<2, false, true>,
+      tc::point_mlp_tc_kernel<1, true, true>,   tc::point_mlp_tc_kernel<2, true, true>};
+  return table[(cg == 2 ? 1 : 0) | (prof ? 2 : 0) | (h16 ? 4 : 0)];
+}
+
 static int tc_cta_group() {
   static int cg = -1;
   if (cg < 0) {
@@ -1296,10 +1336,9 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
     return -2;                         // layers without an ACC-complete signal cannot be dumped
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc::point_mlp_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
-    cudaFuncSetAttribute(tc::point_mlp_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
-    cudaFuncSetAttribute(tc::point_mlp_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
-    cudaFuncSetAttribute(tc::point_mlp_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
+    for (int i = 0; i < 8; ++i)
+      cudaFuncSetAttribute(tc_kernel(1 + (i & 1), (i & 2) != 0, (i & 4) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           tc::kSmemTotal + 1024);
     attr_set = true;
   }
   tc::KernelArgs a;
@@ -1310,6 +1349,7 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
   a.scratch = reinterpret_cast<float*>(workspace);
   a.raw_out = raw_out; a.d_out = w.d_out; a.dbg_sphere = dbg_sphere;
   a.skip_zero = (flags & SRF_FLAG_SKIP_ZERO_CHUNKS) ? 1 : 0;
+  a.hidden_fp16 = (flags & SRF_FLAG_HIDDEN_FP16) ? 1 : 0;
   a.debug_layer = debug_layer; a.debug_acc = debug_acc;
   a.zcache = reinterpret_cast<unsigned char*>(workspace) + (size_t)256 * tc::kTileM * kHidden * sizeof(float);
   if (const char* e = getenv("SRF_TC_ZCACHE")) { if (atoi(e) == 0) a.zcache = nullptr; }
@@ -1345,7 +1385,7 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
     if (!max_pairs) {
       cfg.gridDim = dim3(num_sms() / 2 * 2);
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, tc::point_mlp_tc_kernel<2, false>, &cfg) != cudaSuccess || nc < 1) nc = num_sms() / 2;
+      if (cudaOccupancyMaxActiveClusters(&nc, tc_kernel(2, false, false), &cfg) != cudaSuccess || nc < 1) nc = num_sms() / 2;
       max_pairs = nc;
     }
     max_ctas = max_pairs * 2;
@@ -1367,13 +1407,7 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
         encode_image_map(&tm_out, img + (img_bytes - out_bytes), out_bytes / 128, tc::kOutN / 2))
       a.use_tmap = 1;
   }
-  if (prof_env) {
-    if (cg == 2) cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<2, true>, p, a, tm_main, tm_out);
-    else cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<1, true>, p, a, tm_main, tm_out);
-  } else {
-    if (cg == 2) cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<2, false>, p, a, tm_main, tm_out);
-    else cudaLaunchKernelEx(&cfg, tc::point_mlp_tc_kernel<1, false>, p, a, tm_main, tm_out);
-  }
+  cudaLaunchKernelEx(&cfg, tc_kernel(cg, prof_env, a.hidden_fp16 != 0), p, a, tm_main, tm_out);
   if (prof_env) {            // diagnostics only: synchronises and prints mean per-CTA cycle counters
     static unsigned long long host[256 * 16];
     cudaStreamSynchronize(st);

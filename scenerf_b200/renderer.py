@@ -77,7 +77,8 @@ class B200Renderer:
     """
 
     def __init__(self, hp: dict, mlp_state, mlp_gaussian_state, device="cuda:0", precision: str = "fp16",
-                 rng: str = "philox", skip_zero_chunks: bool = False, pyramid_fp16: bool = True):
+                 rng: str = "philox", skip_zero_chunks: bool = False, pyramid_fp16: bool = True,
+                 hidden_fp16: bool = True):
         if precision not in PRECISIONS:
             raise ValueError("precision must be one of %s" % list(PRECISIONS))
         if rng not in ("torch", "philox"):
@@ -91,6 +92,7 @@ class B200Renderer:
         self.rng = rng
         self.skip_zero_chunks = skip_zero_chunks
         self.pyramid_fp16 = pyramid_fp16      # fp16 mode: store the packed pyramid as fp16 (half the gather bytes)
+        self.hidden_fp16 = hidden_fp16        # fp16 mode: residual hidden state carried between blocks as fp16
         want_tc = precision == "fp16"
         self.mlp = _PackedMlp(mlp_state, 4, self.device, want_tc)
         self.mlp_gaussian = _PackedMlp(mlp_gaussian_state, 2, self.device, want_tc)
@@ -167,7 +169,8 @@ class B200Renderer:
         cfg.T = (C.c_float * 16)(*T.detach().to(torch.float32).reshape(-1).tolist())
         cfg.precision = PRECISIONS[self.precision]
         cfg.seed = self.seed
-        cfg.flags = _lib.FLAG_SKIP_ZERO_CHUNKS if self.skip_zero_chunks else 0
+        cfg.flags = (_lib.FLAG_SKIP_ZERO_CHUNKS if self.skip_zero_chunks else 0) | \
+                    (_lib.FLAG_HIDDEN_FP16 if (self.hidden_fp16 and self.precision == "fp16") else 0)
         return cfg
 
     def _workspace(self, nbytes: int) -> torch.Tensor:

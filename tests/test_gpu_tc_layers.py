@@ -32,7 +32,11 @@ def emulate(cfg, params, pts, viewdir, x_rgb):
     out[1] = acc
     h = acc + b("lin_in.bias") + b("lin_z.0.bias")
     for blk in range(3):
-        acc = q16(np.maximum(h, 0)) @ W("blocks.%d.fc_0.weight" % blk).T
+        # default tensor-core mode (SRF_FLAG_HIDDEN_FP16): the residual hidden state is stored as fp16 between blocks;
+        # the activation fed to fc_0 is relu(h) rounded to fp16, identical with or without that storage rounding
+        h_act = h
+        h = q16(h)
+        acc = q16(np.maximum(h_act, 0)) @ W("blocks.%d.fc_0.weight" % blk).T
         out[2 + 3 * blk] = acc
         net = acc + b("blocks.%d.fc_0.bias" % blk)
         acc = q16(np.maximum(net, 0)) @ W("blocks.%d.fc_1.weight" % blk).T
@@ -127,11 +131,11 @@ def test_fp16_and_fp32_pyramid_storage_agree():
     pts, vd = torch.from_numpy(g["cam_pts"]), torch.from_numpy(g["viewdir"])
     ref = make_renderer(cfg, "fp32").predict("mlp", pts, x_rgb, K, None, vd, output_type="offset").cpu().numpy()
     outs = {}
-    for fp16_pyr in (True, False):
-        r = make_renderer(cfg, "fp16", pyramid_fp16=fp16_pyr)
+    for fp16_pyr, fp16_hid in ((True, True), (False, False), (True, False)):
+        r = make_renderer(cfg, "fp16", pyramid_fp16=fp16_pyr, hidden_fp16=fp16_hid)
         raw, dbg = r.predict("mlp", pts, x_rgb, K, None, vd, output_type="offset", debug=True)
-        outs[fp16_pyr] = (raw.cpu().numpy(), dbg.cpu().numpy())
-    assert (outs[True][1] == outs[False][1]).all()
+        outs[(fp16_pyr, fp16_hid)] = (raw.cpu().numpy(), dbg.cpu().numpy())
+    assert (outs[(True, True)][1] == outs[(False, False)][1]).all()
     scale = max(1.0, np.abs(ref).max())
     for k, (raw, _) in outs.items():
         assert np.abs(raw - ref).max() <= 1e-2 * scale, k
