@@ -168,6 +168,19 @@ int srf_predict(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_wei
                 float* color_dev, int32_t* dbg_sphere_dev, void* workspace_dev, size_t workspace_bytes,
                 void* stream);
 
+/* --- next row: TSDF fusion of the rendered depth sweeps ----------------------------------------------------------
+ * TSDFVolume.integrate of the reference (scenerf/data/utils/fusion.py:219-324, the CPU / numba semantics that
+ * scripts/reconstruction/depth2tsdf.py:87-103 runs): volumes are (dims[0],dims[1],dims[2]) C-order fp32 device arrays
+ * owned by the caller.  srf_tsdf_reset = constructor state (tsdf 255, weight 0, colour 0; fusion.py:55-58).
+ *   origin[3] float32 volume origin; voxel_size; inv_cam_pose_host[16] = inverse(cam_pose) row-major float64 (the
+ *   reference inverts in float64, fusion.py:265); cam_intr_host[9] row-major float32; depth_dev (H,W) float32;
+ *   color_dev (H,W,3) float32 or uint8 (color_is_u8). */
+int srf_tsdf_reset(float* tsdf_dev, float* weight_dev, float* color_dev, const int* dims, void* stream);
+int srf_tsdf_integrate(float* tsdf_dev, float* weight_dev, float* color_dev, const int* dims, const float* origin,
+                       double voxel_size, const double* inv_cam_pose_host, const float* cam_intr_host,
+                       const float* depth_dev, const void* color_dev_im, int color_is_u8, int im_h, int im_w,
+                       double trunc_margin, float obs_weight, void* stream);
+
 /* Diagnostic (not part of the reference-facing surface): run the tensor-core point MLP of srf_predict but stop each
  * 128-point tile after layer `layer` of the tile program (mlp_tc.cu: 1 lin_in+lin_z0, 2 fc0_0, 4 fc1_0+lin_z1,
  * 5 fc0_1, 7 fc1_1+lin_z2, 8 fc0_2, 9 fc1_2, 10 lin_out) and write the raw fp32 accumulator rows to

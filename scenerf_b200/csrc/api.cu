@@ -411,6 +411,28 @@ int srf_predict(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_wei
   return check_cuda("srf_predict");
 }
 
+int srf_tsdf_reset(float* tsdf_dev, float* weight_dev, float* color_dev, const int* dims, void* stream) {
+  if (!tsdf_dev || !weight_dev || !color_dev || !dims || dims[0] < 1 || dims[1] < 1 || dims[2] < 1)
+    return fail(SRF_E_INVALID, "srf_tsdf_reset: bad argument");
+  srf::launch_tsdf_reset(tsdf_dev, weight_dev, color_dev, (long long)dims[0] * dims[1] * dims[2], (cudaStream_t)stream);
+  return check_cuda("srf_tsdf_reset");
+}
+
+int srf_tsdf_integrate(float* tsdf_dev, float* weight_dev, float* color_dev, const int* dims, const float* origin,
+                       double voxel_size, const double* inv_cam_pose_host, const float* cam_intr_host,
+                       const float* depth_dev, const void* color_dev_im, int color_is_u8, int im_h, int im_w,
+                       double trunc_margin, float obs_weight, void* stream) {
+  if (!tsdf_dev || !weight_dev || !color_dev || !dims || !origin || !inv_cam_pose_host || !cam_intr_host || !depth_dev ||
+      !color_dev_im)
+    return fail(SRF_E_INVALID, "srf_tsdf_integrate: NULL argument");
+  if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || im_h < 1 || im_w < 1 || !(voxel_size > 0))
+    return fail(SRF_E_INVALID, "srf_tsdf_integrate: bad shape (%d,%d,%d) image %dx%d voxel %g", dims[0], dims[1], dims[2], im_h, im_w, voxel_size);
+  srf::launch_tsdf_integrate(dims, origin, voxel_size, inv_cam_pose_host, cam_intr_host, im_h, im_w, trunc_margin, obs_weight,
+                             color_is_u8, tsdf_dev, weight_dev, color_dev, depth_dev, color_dev_im, (cudaStream_t)stream);
+  g_launches = 1;
+  return check_cuda("srf_tsdf_integrate");
+}
+
 int srf_debug_tc_layer(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w,
                        const float* cam_pts_dev, const float* viewdir_dev, int n_cols, int n_per, int layer,
                        float* acc_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {

@@ -17,6 +17,12 @@ void launch_composite_som(const DevParams& p, int R, const float* raw, const flo
 // pack.cu
 void launch_chw_to_hwc(const float* src, void* dst, int C, int H, int W, bool fp16, cudaStream_t st);
 
+// tsdf.cu : TSDF integration of rendered depth sweeps (reference: data/utils/fusion.py:219-324, CPU path)
+void launch_tsdf_reset(float* tsdf, float* weight, float* color, long long n, cudaStream_t st);
+void launch_tsdf_integrate(const int* dims, const float* origin, double voxel_size, const double* inv_pose, const float* intr,
+                           int im_h, int im_w, double trunc, float obs_weight, int color_is_u8, float* tsdf, float* weight,
+                           float* color, const float* depth, const void* color_im, cudaStream_t st);
+
 // mlp_simt.cu : float32 point MLP (gather + positional encoding + ResnetFC), n points in chunks.
 //   pts (n,3) infer-frame points; viewdir (n/n_per,3); raw_out (n,d_out).  Returns number of kernel launches.
 size_t simt_workspace_bytes(int d_latent, int n_points);

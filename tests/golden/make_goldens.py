@@ -274,6 +274,43 @@ def predict_adversarial_bf():
     return run_predict_case(cfg, pts, vd, pyr_seed=37)
 
 
+def tsdf_inputs():
+    """Synthetic depth sweep for the TSDF golden: 3 poses (sample_rel_poses style), small images, scaled intrinsics."""
+    H, W = 48, 160
+    K = np.array([[707.0912 * W / 1220.0, 0, 601.8873 * W / 1220.0], [0, 707.0912 * H / 370.0, 183.1104 * H / 370.0], [0, 0, 1]])
+    T_velo2cam = np.array([[0.0, -1.0, 0.0, 0.0], [0.0, 0.0, -1.0, -0.08], [1.0, 0.0, 0.0, -0.27], [0, 0, 0, 1.0]])
+    frames = []
+    for i, (yaw, tz) in enumerate(((0.0, 0.0), (10.0, 1.5), (-10.0, 3.0))):
+        depth = (4.0 + 6.0 * synth.hash_unit(50 + i, H * W).reshape(H, W) + np.linspace(0, 4, W)[None, :]).astype(np.float32)
+        depth[synth.hash_unit(60 + i, H * W).reshape(H, W) < 0.05] = 0.0           # holes
+        rgb = np.floor(synth.hash_unit(70 + i, H * W * 3).reshape(H, W, 3) * 256.0).astype(np.float64)
+        rel = synth.yaw_translate(yaw, tz).astype(np.float64)
+        frames.append((rgb, depth, np.linalg.inv(T_velo2cam) @ rel))
+    vol_bnds = np.zeros((3, 2))
+    vol_bnds[:, 0] = [0, -6.4, -2]
+    vol_bnds[:, 1] = vol_bnds[:, 0] + [12.8, 12.8, 3.2]
+    return K, frames, vol_bnds
+
+
+@case
+def tsdf_fusion():
+    """The reference's TSDFVolume (CPU / numba path, fusion.py:219-324) on a 3-pose synthetic depth sweep."""
+    sk = types.ModuleType("skimage")
+    sk.measure = types.ModuleType("skimage.measure")
+    sys.modules.setdefault("skimage", sk)
+    sys.modules.setdefault("skimage.measure", sk.measure)
+    import scenerf.data.utils.fusion as fusion
+    K, frames, vol_bnds = tsdf_inputs()
+    vol = fusion.TSDFVolume(vol_bnds.copy(), voxel_size=0.2, trunc_margin=10, use_gpu=False)
+    out = {}
+    for i, (rgb, depth, pose) in enumerate(frames):
+        vol.integrate(rgb, depth, K, pose, obs_weight=1.)
+        out["rgb%d" % i], out["depth%d" % i], out["pose%d" % i] = rgb.astype(np.float32), depth, pose
+    tsdf, color = vol.get_volume()
+    out.update(K=K, vol_bnds=vol_bnds, tsdf=tsdf.copy(), color=color.copy(), weight=vol._weight_vol_cpu.copy())
+    return out
+
+
 @case
 def angles_kat():
     """The only known-answer check in the reference: scripts/determine_angles.py <-> scenerf.py:84-87 and
