@@ -314,7 +314,7 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "point_mlp_tc_kernel (main pass)" if args.precision == "fp16" else "sgemm_nt_kernel chain",
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/traffic.json)", "kernel": "point_mlp_tc_kernel (main pass)" if args.precision == "fp16" else "sgemm_nt_kernel chain",
                 "kernel_ms": main_ms, "algorithmic_flop_per_launch": flop_launch, "peak_source": peak_src,
                 "whole_step_tflops": world * R * flop_per_ray(cfg) / (ms_per_step * 1e-3) / 1e12}
 
