@@ -181,6 +181,21 @@ int srf_tsdf_integrate(float* tsdf_dev, float* weight_dev, float* color_dev, con
                        const float* depth_dev, const void* color_dev_im, int color_is_u8, int im_h, int im_w,
                        double trunc_margin, float obs_weight, void* stream);
 
+/* Merge volume B into A (same dims) with integrate's fold rule: keep A where |A| < |B|, else B's distance and colour;
+ * weights add.  Used when the poses of one sweep are integrated on several GPUs: merging the ranks' volumes in pose
+ * order equals integrating all poses sequentially (fusion.py:212-216). */
+int srf_tsdf_merge(float* tsdf_a, float* weight_a, float* color_a, const float* tsdf_b, const float* weight_b,
+                   const float* color_b, const int* dims, void* stream);
+
+/* --- next row: image-side glue of the novel-view sweep (scripts/reconstruction/generate_novel_depths.py:103-152) ---
+ * The reference renders an x-major stride-`scale` pixel grid (gw x gh rays, ray = ix*gh + iy), reshapes, transposes
+ * and F.interpolate(bilinear)s to (H,W).  srf_upsample_render does that in one pass from the render outputs:
+ * depth_xm (gw*gh) -> depth_out (H,W); color_xm (gw*gh,3) -> color_out (H,W,3).  Either pair may be NULL.
+ * gw==W && gh==H is the scale-1 case (transpose only).  color_mode: 0 raw, 1 clamp to [0,1] (:144),
+ * 2 = the PNG round trip the reference's TSDF stage sees: float32(uint8(c*255))/255*255 (depth2tsdf.py:19-26,98). */
+int srf_upsample_render(const float* depth_xm, const float* color_xm, int gw, int gh, int out_h, int out_w,
+                        float* depth_out, float* color_out, int color_mode, void* stream);
+
 /* Diagnostic (not part of the reference-facing surface): run the tensor-core point MLP of srf_predict but stop each
  * 128-point tile after layer `layer` of the tile program (mlp_tc.cu: 1 lin_in+lin_z0, 2 fc0_0, 4 fc1_0+lin_z1,
  * 5 fc0_1, 7 fc1_1+lin_z2, 8 fc0_2, 9 fc1_2, 10 lin_out) and write the raw fp32 accumulator rows to

@@ -433,6 +433,28 @@ int srf_tsdf_integrate(float* tsdf_dev, float* weight_dev, float* color_dev, con
   return check_cuda("srf_tsdf_integrate");
 }
 
+int srf_tsdf_merge(float* tsdf_a, float* weight_a, float* color_a, const float* tsdf_b, const float* weight_b,
+                   const float* color_b, const int* dims, void* stream) {
+  if (!tsdf_a || !weight_a || !color_a || !tsdf_b || !weight_b || !color_b || !dims || dims[0] < 1 || dims[1] < 1 || dims[2] < 1)
+    return fail(SRF_E_INVALID, "srf_tsdf_merge: bad argument");
+  srf::launch_tsdf_merge(tsdf_a, weight_a, color_a, tsdf_b, weight_b, color_b, (long long)dims[0] * dims[1] * dims[2],
+                         (cudaStream_t)stream);
+  g_launches = 1;
+  return check_cuda("srf_tsdf_merge");
+}
+
+int srf_upsample_render(const float* depth_xm, const float* color_xm, int gw, int gh, int out_h, int out_w,
+                        float* depth_out, float* color_out, int color_mode, void* stream) {
+  if (gw < 1 || gh < 1 || out_h < 1 || out_w < 1 || color_mode < 0 || color_mode > 2)
+    return fail(SRF_E_INVALID, "srf_upsample_render: bad shape grid %dx%d -> %dx%d mode %d", gw, gh, out_w, out_h, color_mode);
+  if ((!depth_xm || !depth_out) && (!color_xm || !color_out))
+    return fail(SRF_E_INVALID, "srf_upsample_render: nothing to do (need a depth pair or a colour pair)");
+  srf::launch_upsample_render(depth_out ? depth_xm : nullptr, color_out ? color_xm : nullptr, gw, gh, out_h, out_w, depth_out,
+                              color_out, color_mode, (cudaStream_t)stream);
+  g_launches = 1;
+  return check_cuda("srf_upsample_render");
+}
+
 int srf_debug_tc_layer(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w,
                        const float* cam_pts_dev, const float* viewdir_dev, int n_cols, int n_per, int layer,
                        float* acc_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {

@@ -23,6 +23,12 @@ void launch_tsdf_integrate(const int* dims, const float* origin, double voxel_si
                            int im_h, int im_w, double trunc, float obs_weight, int color_is_u8, float* tsdf, float* weight,
                            float* color, const float* depth, const void* color_im, cudaStream_t st);
 
+// image_ops.cu : resampling of x-major renders into images, TSDF volume merge
+void launch_upsample_render(const float* depth_xm, const float* color_xm, int gw, int gh, int H, int W, float* depth_out,
+                            float* color_out, int color_mode, cudaStream_t st);
+void launch_tsdf_merge(float* tsdf_a, float* weight_a, float* color_a, const float* tsdf_b, const float* weight_b,
+                       const float* color_b, long long n, cudaStream_t st);
+
 // mlp_simt.cu : float32 point MLP (gather + positional encoding + ResnetFC), n points in chunks.
 //   pts (n,3) infer-frame points; viewdir (n/n_per,3); raw_out (n,d_out).  Returns number of kernel launches.
 size_t simt_workspace_bytes(int d_latent, int n_points);

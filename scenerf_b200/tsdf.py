@@ -55,6 +55,16 @@ class TSDFVolume:
             col.data_ptr(), 1 if is_u8 else 0, int(im_h), int(im_w), float(self._trunc_margin), float(obs_weight),
             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
 
+    def merge_(self, tsdf, weight, color):
+        """Fold another volume's state (later observations) into this one: include/scenerf_b200.h srf_tsdf_merge."""
+        t, w, c = (x.to(device=self.device, dtype=torch.float32).contiguous() for x in (tsdf, weight, color))
+        if tuple(t.shape) != tuple(self._tsdf.shape):
+            raise ValueError("volume shape mismatch %s vs %s" % (tuple(t.shape), tuple(self._tsdf.shape)))
+        _lib.check(self.lib.srf_tsdf_merge(self._tsdf.data_ptr(), self._weight.data_ptr(), self._color.data_ptr(), t.data_ptr(),
+                                           w.data_ptr(), c.data_ptr(), self._dims,
+                                           C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return self
+
     def get_volume(self):
         return self._tsdf.cpu().numpy(), self._color.cpu().numpy()
 

@@ -311,6 +311,89 @@ def tsdf_fusion():
     return out
 
 
+def sweep_setup():
+    """Small-image stand-in of generate_novel_depths.py: 244x74 image (KITTI intrinsics / 5), stride-4 grid (61x19 rays),
+    the 6 poses of sample_rel_poses(step=1.0, angle=10, max_distance=1.1)."""
+    cfg = synth.config_A(name="sweep_kitti", sphere_W=300, sphere_H=90)
+    cfg.img_W, cfg.img_H = 244, 74
+    cfg.K = synth.KITTI_K.copy()
+    cfg.K[:2] /= 5.0
+    return cfg, 4, dict(step=1.0, angle=10, max_distance=1.1), 39
+
+
+@case
+def sweep_kitti():
+    """generate_novel_depths.py:52,103-152 + depth2tsdf.py:87-103 run with the reference's own functions on a small image."""
+    import torch.nn.functional as F
+    _install_shims()
+    from scenerf.models.utils import sample_rel_poses, sample_rel_poses_bf
+    sk = types.ModuleType("skimage")
+    sk.measure = types.ModuleType("skimage.measure")
+    sys.modules.setdefault("skimage", sk)
+    sys.modules.setdefault("skimage.measure", sk.measure)
+    import scenerf.data.utils.fusion as fusion
+    cfg, scale, pose_kw, pyr_seed = sweep_setup()
+    out = {}
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        bf = sample_rel_poses_bf(angle=15, max_distance=0.7, step=0.2)
+    out["bf_pose_keys"] = np.array([[float(s), float(a)] for s, a in bf.keys()], dtype=np.float64)
+    out["bf_poses"] = np.stack([v.numpy() for v in bf.values()])
+    full = sample_rel_poses(step=0.5, angle=10, max_distance=10.1)
+    out["full_pose_keys"] = np.array([[float(s), float(a)] for s, a in full.keys()], dtype=np.float64)
+    out["full_poses"] = np.stack([v.numpy() for v in full.values()])
+    rel_poses = sample_rel_poses(**pose_kw)
+    out["pose_keys"] = np.array([[float(s), float(a)] for s, a in rel_poses.keys()], dtype=np.float64)
+    out["poses"] = np.stack([v.numpy() for v in rel_poses.values()])
+
+    model = build_reference_model(cfg)
+    x_rgb = {k: torch.from_numpy(v) for k, v in synth.make_pyramid(pyr_seed, cfg.sphere_W, cfg.sphere_H).items()}
+    cam_K = torch.from_numpy(cfg.K)
+    img_size = (cfg.img_W, cfg.img_H)
+    T_velo2cam = np.array([[0.0, -1.0, 0.0, 0.0], [0.0, 0.0, -1.0, -0.08], [1.0, 0.0, 0.0, -0.27], [0, 0, 0, 1.0]])
+    vol_bnds = np.zeros((3, 2))
+    vol_bnds[:, 0] = [0, -6.4, -2]
+    vol_bnds[:, 1] = vol_bnds[:, 0] + [12.8, 12.8, 3.2]
+    vol = fusion.TSDFVolume(vol_bnds.copy(), voxel_size=0.2, use_gpu=False)
+    torch.manual_seed(0)
+    for i, ((step, angle), rel_pose) in enumerate(rel_poses.items()):
+        # generate_novel_depths.py:103-147, verbatim sequence of torch calls
+        xs = torch.arange(start=0, end=img_size[0], step=scale).type_as(cam_K)
+        ys = torch.arange(start=0, end=img_size[1], step=scale).type_as(cam_K)
+        grid_x, grid_y = torch.meshgrid(xs, ys)
+        rendered_im_size = grid_x.shape
+        sampled_pixels = torch.cat([grid_x.unsqueeze(-1), grid_y.unsqueeze(-1)], dim=2).reshape(-1, 2)
+        with torch.no_grad(), _Recorder(model) as r:
+            rd = model.render_rays_batch(cam_K, rel_pose.type_as(cam_K), x_rgb, ray_batch_size=5000,
+                                         sampled_pixels=sampled_pixels)
+        depth_rendered = rd["depth"].reshape(rendered_im_size[0], rendered_im_size[1])
+        color_rendered = rd["color"].reshape(rendered_im_size[0], rendered_im_size[1], 3)
+        depth_rendered = F.interpolate(depth_rendered.T.unsqueeze(0).unsqueeze(0), size=(img_size[1], img_size[0]), mode="bilinear")
+        color_rendered = F.interpolate(color_rendered.permute(2, 1, 0).unsqueeze(0), size=(img_size[1], img_size[0]), mode="bilinear")
+        color_np = color_rendered.clamp(0, 1).squeeze().permute(2, 1, 0).detach().cpu().numpy()
+        color_np = np.transpose(color_np, (1, 0, 2))
+        depth_np = depth_rendered.squeeze().detach().cpu().numpy()
+        # plt.imsave (matplotlib ScalarMappable.to_rgba(bytes=True): (x*255).astype(uint8)); PNG is lossless;
+        # depth2tsdf.py:19-26,98 reads it back as float32/255.0 and multiplies by 255.0
+        u8 = (color_np * 255).astype(np.uint8)
+        rgb = (np.array(u8, dtype=np.float32) / 255.0) * 255.0
+        vol.integrate(rgb, depth_np, cfg.K, np.linalg.inv(T_velo2cam) @ rel_pose.numpy(), obs_weight=1.)
+        R = sampled_pixels.shape[0]
+        out["noise_u%d" % i] = r.rec["noise_u"][0].reshape(R, -1).numpy()
+        out["noise_n%d" % i] = r.rec["noise_n"][0].reshape(R, -1).numpy()
+        out["depth_rays%d" % i], out["color_rays%d" % i] = rd["depth"].numpy(), rd["color"].numpy()
+        if i in (0, 4):           # full images only for two poses (fixture size)
+            out["depth%d" % i], out["color%d" % i], out["rgb_tsdf%d" % i] = depth_np, color_np.astype(np.float16), u8
+    tsdf, color = vol.get_volume()
+    out.update(pixels=sampled_pixels.numpy(), K=cfg.K, T_velo2cam=T_velo2cam, vol_bnds=vol_bnds, tsdf=tsdf.copy(),
+               tsdf_color=color.copy(), tsdf_weight=vol._weight_vol_cpu.copy())
+    # a non-integer-ratio resampling case for the interpolation restatement (stride 3 grid of a 50x23 image)
+    g = torch.from_numpy(synth.hash_normalish(77, 17 * 8).reshape(17, 8).astype(np.float32))
+    out["interp_src"] = g.numpy()
+    out["interp_dst"] = F.interpolate(g.T.unsqueeze(0).unsqueeze(0), size=(23, 50), mode="bilinear").squeeze().numpy()
+    return out
+
+
 @case
 def angles_kat():
     """The only known-answer check in the reference: scripts/determine_angles.py <-> scenerf.py:84-87 and
