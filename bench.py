@@ -189,13 +189,117 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def run_sweep(args, rank, world, local):
+    """--workload sweep: the reconstruction rows (SURVEY 8f-2 TSDF integrate, 8f-4 novel-view sweep).  One "step" = the
+    sweep of one source frame with the defaults of generate_novel_depths.py / depth2tsdf.py: 1220x370 image, stride 2,
+    63 poses, 64 samples per ray, 256x256x32 TSDF volume; with N GPUs the poses are sharded and the volumes merged.
+    Not the headline metric: a second JSON line format with the TSDF kernel's HBM roofline and the reference's CPU TSDF
+    path (oracle restatement) timed beside it."""
+    import time
+    import torch
+    import torch.distributed as dist
+    from scenerf_b200 import synth, sweep
+    from scenerf_b200.renderer import B200Renderer
+    from scenerf_b200.tsdf import TSDFVolume
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = synth.config_A(name="sweep")                     # KITTI class defaults: 64 samples/ray, sphere 1500x452
+    pm, pg = synth.make_model_params(cfg)
+    to = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    r = B200Renderer(hp_from_cfg(cfg), to(pm), to(pg), device=dev, precision="fp16")
+    x_rgb = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_pyramid(3, cfg.sphere_W, cfg.sphere_H).items()}
+    cam_K = torch.from_numpy(synth.KITTI_K).to(dev)
+    sw = sweep.NovelDepthSweep(r, cam_K, x_rgb, img_size=(1220, 370), scale=args.sweep_scale)
+    poses = dict(list(sweep.sample_rel_poses(step=0.5, angle=10, max_distance=10.1).items())[:args.sweep_poses])
+    T_velo2cam = np.array([[0.0, -1.0, 0.0, 0.0], [0.0, 0.0, -1.0, -0.08], [1.0, 0.0, 0.0, -0.27], [0, 0, 0, 1.0]])
+    vol_bnds = np.zeros((3, 2))
+    vol_bnds[:, 0] = [0, -25.6, -2]
+    vol_bnds[:, 1] = vol_bnds[:, 0] + [51.2, 51.2, 6.4]
+
+    def frame():
+        return sw.reconstruct(poses, T_velo2cam, vol_bnds, voxel_size=0.2, rank=rank, world=world)
+
+    for _ in range(args.warmup):
+        vol = frame()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sw.launches = 0
+    e0.record()
+    for _ in range(args.steps):
+        vol = frame()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # --- the TSDF kernel alone, against HBM ------------------------------------------------------------------------
+    depth, rgb = sw.render(list(poses.values())[1].to(cam_K), sweep.COLOR_PNG)
+    tv = TSDFVolume(vol_bnds, voxel_size=0.2, device=dev)
+    pose = np.linalg.inv(T_velo2cam) @ list(poses.values())[1].numpy().astype(np.float64)
+    n_it = 200
+    for _ in range(5):
+        tv.integrate(rgb, depth, synth.KITTI_K, pose)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n_it):
+        tv.integrate(rgb, depth, synth.KITTI_K, pose)
+    e1.record()
+    torch.cuda.synchronize()
+    tsdf_us = e0.elapsed_time(e1) / n_it * 1e3
+    n_vox = int(np.prod(tv._vol_dim))
+    touched = float((tv.get_weight() > 0).mean())
+    # algorithmic bytes per launch: every voxel is projected (no memory), touched voxels read tsdf+weight (8 B), write
+    # weight (4 B) and, when the new observation wins (all of them on a repeat of the same frame), tsdf+colour (8 B),
+    # plus the depth/colour pixel (16 B, L2-resident image of 7.2 MB counted once)
+    alg_bytes = n_vox * touched * (8 + 4 + 8) + depth.numel() * 16
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs") or 6500.0)
+
+    out = {"metric": "sweep frames/sec (one source frame: %d poses rendered at stride %d + TSDF fusion)" % (len(poses), args.sweep_scale),
+           "value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "rays_per_pose": int(sw.pixels.shape[0]), "samples_per_ray": cfg.S, "poses": len(poses),
+           "rays_per_sec": len(poses) * int(sw.pixels.shape[0]) / (ms * 1e-3), "gpu_launches": sw.launches // max(1, args.steps),
+           "volume": [int(d) for d in tv._vol_dim], "volume_touched_frac": float((vol.get_weight() > 0).mean()),
+           "tsdf_kernel": {"us_per_launch": tsdf_us, "algorithmic_bytes": alg_bytes, "achieved_gbps": alg_bytes / (tsdf_us * 1e-6) / 1e9,
+                           "peak_gbps": hbm, "frac": alg_bytes / (tsdf_us * 1e-6) / 1e9 / hbm, "touched_frac": touched,
+                           "note": "includes the host-side 4x4 inverse + ctypes call of TSDFVolume.integrate; 2.1 M voxels is launch-latency bound"}}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle.tsdf_oracle import TSDFVolumeOracle
+        ov = TSDFVolumeOracle(vol_bnds, 0.2, 10)
+        d_np, c_np = depth.cpu().numpy(), rgb.cpu().numpy()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ov.integrate(c_np, d_np, synth.KITTI_K, pose, 1.0)
+        out["tsdf_cpu_baseline"] = {"ms_per_integrate": (time.perf_counter() - t0) / 3 * 1e3, "kind": "port", "cores": 1,
+                                    "sample": "3 integrations of one 1220x370 frame into the 256x256x32 volume (numpy restatement of fusion.py CPU path)"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="B", choices=["A", "B", "C"])
+    ap.add_argument("--workload", default="B", choices=["A", "B", "C", "sweep"])
+    ap.add_argument("--sweep-poses", type=int, default=63)
+    ap.add_argument("--sweep-scale", type=int, default=2)
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--skip-zero-chunks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -206,6 +310,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "sweep":
+        run_sweep(args, rank, world, local_rank)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

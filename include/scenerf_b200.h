@@ -183,7 +183,8 @@ int srf_tsdf_integrate(float* tsdf_dev, float* weight_dev, float* color_dev, con
 
 /* Merge volume B into A (same dims) with integrate's fold rule: keep A where |A| < |B|, else B's distance and colour;
  * weights add.  Used when the poses of one sweep are integrated on several GPUs: merging the ranks' volumes in pose
- * order equals integrating all poses sequentially (fusion.py:212-216). */
+ * order equals integrating all poses sequentially (fusion.py:212-216): distances and weights bit for bit, colours
+ * except on float32-exact distance ties between observations of different ranks (either minimal observation). */
 int srf_tsdf_merge(float* tsdf_a, float* weight_a, float* color_a, const float* tsdf_b, const float* weight_b,
                    const float* color_b, const int* dims, void* stream);
 

@@ -68,7 +68,9 @@ __global__ void upsample_render_kernel(const float* __restrict__ depth_xm, const
 
 // Merge volume B (later observations) into A (earlier ones) with the fold rule of fusion.py:212-216: keep A where
 // |A| < |B|, else take B's distance and colour; weights add.  Contiguous pose ranges merged in order reproduce the
-// sequential integration exactly (the last observation among equal minima wins in both).
+// sequential integration: distances and weights bit for bit; the colour can differ only where two observations from
+// different ranges have distances that round to the same float32 (the sequential fold compares the stored float32
+// with the incoming float64, the merge sees two float32) -- both answers are an observation of minimal |distance|.
 __global__ void tsdf_merge_kernel(float* __restrict__ tsdf_a, float* __restrict__ weight_a, float* __restrict__ color_a,
                                   const float* __restrict__ tsdf_b, const float* __restrict__ weight_b,
                                   const float* __restrict__ color_b, long long n) {

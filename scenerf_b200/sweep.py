@@ -99,7 +99,8 @@ class NovelDepthSweep:
                     rank: int = 0, world: int = 1, group=None) -> TSDFVolume:
         """Integrate the sweep into a TSDF volume.  With world > 1 every rank renders a contiguous range of the poses
         into its own volume and the volumes are merged in rank order (== pose order), which reproduces the sequential
-        integration exactly; every rank returns the merged volume."""
+        integration (distances and weights bit for bit; colours up to float32-exact distance ties, see
+        csrc/image_ops.cu); every rank returns the merged volume."""
         from .dist import shard_range
         items = list(rel_poses.items())
         lo, hi, _ = shard_range(len(items), rank, world)

@@ -12,12 +12,12 @@ def hp_from_cfg(cfg):
                 v_angle_max=v_max, h_angle_min=h_min, h_angle_max=h_max)
 
 
-def make_renderer(cfg, precision, **kw):
+def make_renderer(cfg, precision, device="cuda:0", **kw):
     import torch
     from scenerf_b200.renderer import B200Renderer
     pm, pg = params_for(cfg)
     to = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
-    return B200Renderer(hp_from_cfg(cfg), to(pm), to(pg), device="cuda:0", precision=precision, **kw)
+    return B200Renderer(hp_from_cfg(cfg), to(pm), to(pg), device=device, precision=precision, **kw)
 
 
 def torch_pyramid(cfg, seed, device="cuda:0"):
