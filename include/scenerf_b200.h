@@ -168,6 +168,27 @@ int srf_predict(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_wei
                 float* color_dev, int32_t* dbg_sphere_dev, void* workspace_dev, size_t workspace_bytes,
                 void* stream);
 
+/* --- next row: backward pass (training drop-in) ----------------------------------------------------------------------
+ * What torch.autograd computes for SceneRF.render_rays_batch (scenerf.py:392-748; consumers of the gradients: the losses
+ * of scenerf.py:243-320).  float32 precision and an SRF_PYR_FP32 pyramid only.  Call srf_render_rays first with ALL 12
+ * dict outputs plus `som_means` requested and keep its workspace untouched: the backward reads the forward's
+ * intermediates (sorted distances, sample points, raw MLP outputs) from it.
+ *   noise_n_dev     : the same (R,G*P) tensor the forward got, or NULL when the forward drew Philox noise (same cfg->seed)
+ *   fwd_out         : the forward's outputs;  grad_out: cotangents with the same shapes, NULL members = zero.
+ *                     `som_vars` cotangents are ignored: RaySOM statistics are not differentiated (their only consumer logs
+ *                     them detached, scenerf.py:222-227); everything else matches autograd (scenerf.py:662 detach included).
+ *   grad_main/gauss : float32 device buffers shaped like the weights (srf_mlp_weights used as a pointer table, packed_tc
+ *                     ignored); gradients are ACCUMULATED into them (zero them for a fresh gradient).
+ *   grad_pyr_chw[5] : float32 CHW buffers shaped like the caller's feature maps; accumulated with atomics.
+ * Parameter gradients are bit-reproducible run to run; feature-map gradients up to float atomics ordering. */
+size_t srf_render_backward_workspace_bytes(const srf_config* cfg, int n_rays);
+int srf_render_rays_backward(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w_main,
+                             const srf_mlp_weights* w_gauss, int n_rays, const float* noise_n_dev,
+                             const srf_outputs* fwd_out, const srf_outputs* grad_out, const void* fwd_workspace_dev,
+                             size_t fwd_workspace_bytes, const srf_mlp_weights* grad_main,
+                             const srf_mlp_weights* grad_gauss, float* const* grad_pyr_chw, void* workspace_dev,
+                             size_t workspace_bytes, void* stream);
+
 /* --- next row: TSDF fusion of the rendered depth sweeps ----------------------------------------------------------
  * TSDFVolume.integrate of the reference (scenerf/data/utils/fusion.py:219-324, the CPU / numba semantics that
  * scripts/reconstruction/depth2tsdf.py:87-103 runs): volumes are (dims[0],dims[1],dims[2]) C-order fp32 device arrays

@@ -82,6 +82,11 @@ SYMBOLS = {
     "srf_predict": (C.c_int, [C.POINTER(Config), C.POINTER(Pyramid), C.POINTER(MlpWeights), C.c_void_p, C.c_void_p,
                               C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_size_t, C.c_void_p]),
+    "srf_render_backward_workspace_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int]),
+    "srf_render_rays_backward": (C.c_int, [C.POINTER(Config), C.POINTER(Pyramid), C.POINTER(MlpWeights), C.POINTER(MlpWeights),
+                                           C.c_int, C.c_void_p, C.POINTER(Outputs), C.POINTER(Outputs), C.c_void_p, C.c_size_t,
+                                           C.POINTER(MlpWeights), C.POINTER(MlpWeights), C.POINTER(C.c_void_p), C.c_void_p,
+                                           C.c_size_t, C.c_void_p]),
     "srf_tsdf_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     "srf_tsdf_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_double,
                                      C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_int, C.c_int,

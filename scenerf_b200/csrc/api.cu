@@ -411,6 +411,73 @@ int srf_predict(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_wei
   return check_cuda("srf_predict");
 }
 
+size_t srf_render_backward_workspace_bytes(const srf_config* cfg, int n_rays) {
+  if (!cfg || n_rays < 0) return 0;
+  const size_t G = cfg->n_gaussians, S = cfg->n_pts_uni + G * cfg->n_pts_per_gaussian;
+  const int d_latent = cfg->d_latent > 0 ? cfg->d_latent : kDefaultLatent;
+  const size_t m1 = srf::mlp_backward_workspace_bytes(d_latent, (int)((size_t)n_rays * S));
+  const size_t m2 = srf::mlp_backward_workspace_bytes(d_latent, (int)((size_t)n_rays * G));
+  return align256((size_t)n_rays * S * 4 * 4) + align256((size_t)n_rays * G * 2 * 4) + (m1 > m2 ? m1 : m2) + 4096;
+}
+
+int srf_render_rays_backward(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w_main,
+                             const srf_mlp_weights* w_gauss, int n_rays, const float* noise_n_dev,
+                             const srf_outputs* fwd_out, const srf_outputs* grad_out, const void* fwd_workspace_dev,
+                             size_t fwd_workspace_bytes, const srf_mlp_weights* grad_main,
+                             const srf_mlp_weights* grad_gauss, float* const* grad_pyr_chw, void* workspace_dev,
+                             size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  if (int rc = validate(cfg, pyr)) return rc;
+  if (!pyr || !fwd_out || !grad_out || !grad_main || !grad_gauss || !grad_pyr_chw)
+    return fail(SRF_E_INVALID, "srf_render_rays_backward: NULL argument");
+  if (cfg->precision != SRF_PREC_FP32 || pyr->format != SRF_PYR_FP32)
+    return fail(SRF_E_INVALID, "srf_render_rays_backward: float32 precision and an fp32 pyramid are required");
+  if (n_rays == 0) return SRF_OK;
+  if (n_rays < 0) return fail(SRF_E_INVALID, "srf_render_rays_backward: n_rays=%d", n_rays);
+  if (!fwd_out->depth || !fwd_out->alphas || !fwd_out->weights || !fwd_out->densities || !fwd_out->depth_volumes ||
+      !fwd_out->gaussian_means || !fwd_out->gaussian_stds || !fwd_out->som_vars || !fwd_out->som_means)
+    return fail(SRF_E_INVALID, "srf_render_rays_backward: the forward must have produced depth, alphas, weights, densities, "
+                               "depth_volumes, gaussian_means, gaussian_stds, som_vars and som_means");
+  const int d_latent = pyramid_channels(pyr);
+  if (int rc = validate_weights(w_main, 4, d_latent, cfg->precision)) return rc;
+  if (int rc = validate_weights(w_gauss, 2, d_latent, cfg->precision)) return rc;
+  if (int rc = validate_weights(grad_main, 4, d_latent, cfg->precision)) return rc;
+  if (int rc = validate_weights(grad_gauss, 2, d_latent, cfg->precision)) return rc;
+  for (int s = 0; s < SRF_NUM_SCALES; ++s)
+    if (!grad_pyr_chw[s]) return fail(SRF_E_INVALID, "srf_render_rays_backward: grad_pyr_chw[%d] is NULL", s);
+  RayWorkspace fw;
+  const size_t fneed = carve(cfg, n_rays, d_latent, reinterpret_cast<unsigned char*>(const_cast<void*>(fwd_workspace_dev)), &fw);
+  if (!fwd_workspace_dev || fwd_workspace_bytes < fneed)
+    return fail(SRF_E_WORKSPACE, "srf_render_rays_backward: forward workspace has %zu bytes, need %zu", fwd_workspace_bytes, fneed);
+  srf_config c2 = *cfg;
+  c2.d_latent = d_latent;
+  const size_t need = srf_render_backward_workspace_bytes(&c2, n_rays);
+  if (!workspace_dev || workspace_bytes < need)
+    return fail(SRF_E_WORKSPACE, "srf_render_rays_backward: workspace has %zu bytes, need %zu", workspace_bytes, need);
+  const cudaStream_t st = (cudaStream_t)stream;
+  const srf::DevParams p = make_params(cfg, pyr);
+  const int R = n_rays, G = p.G, S = p.S;
+  Arena a{reinterpret_cast<unsigned char*>(workspace_dev), 0, 0};
+  float* graw_main = a.take<float>((size_t)R * S * 4);
+  float* graw_gauss = a.take<float>((size_t)R * G * 2);
+  const size_t mlp_ws_bytes = workspace_bytes - a.off - 2048;
+  void* mlp_ws = a.take<unsigned char>(mlp_ws_bytes);
+  srf::launch_ray_backward(p, R, fw.raw, fw.t_sorted, fw.unit, fw.gauss_raw, noise_n_dev, *fwd_out, *grad_out, graw_main,
+                           graw_gauss, st);
+  ++g_launches;
+  if (int rc = check_cuda("ray_backward")) return rc;
+  int l = srf::run_point_mlp_backward_simt(p, *w_main, *grad_main, grad_pyr_chw, fw.pts, fw.viewdir, R * S, S, graw_main, mlp_ws,
+                                           mlp_ws_bytes, st);
+  if (l < 0) return fail(SRF_E_WORKSPACE, "srf_render_rays_backward: MLP backward workspace too small");
+  g_launches += l;
+  if (int rc = check_cuda("main MLP backward")) return rc;
+  l = srf::run_point_mlp_backward_simt(p, *w_gauss, *grad_gauss, grad_pyr_chw, fw.gauss_pts, fw.viewdir, R * G, G, graw_gauss,
+                                       mlp_ws, mlp_ws_bytes, st);
+  if (l < 0) return fail(SRF_E_WORKSPACE, "srf_render_rays_backward: MLP backward workspace too small");
+  g_launches += l;
+  return check_cuda("gaussian MLP backward");
+}
+
 int srf_tsdf_reset(float* tsdf_dev, float* weight_dev, float* color_dev, const int* dims, void* stream) {
   if (!tsdf_dev || !weight_dev || !color_dev || !dims || dims[0] < 1 || dims[1] < 1 || dims[2] < 1)
     return fail(SRF_E_INVALID, "srf_tsdf_reset: bad argument");

@@ -1,0 +1,425 @@
+// Backward pass of the ray-render path ("next" row 8f-1 of the hot-path contract): what torch.autograd computes for
+// SceneRF.render_rays_batch (scenerf/models/scenerf.py:392-748), hand-written.  float32 SIMT, the backward twin of
+// mlp_simt.cu / ray_kernels.cu (strict mode); a tensor-core backward is the follow-up.
+//
+// Gradient structure (forward op file:line -> what is differentiated):
+//   scenerf.py:662      main-MLP inputs detached: no gradient into sample positions through the MLP
+//   utils.py:204-214    t = mean + eps*std (clamped at 0.1: clamped samples carry no gradient), depth_volume = t*unit_z
+//   scenerf.py:704-748  compositing (cumprod backward as torch: reverse cumsum of grad*out divided by the input)
+//   ray_som_kl.py:64-92 loss_kl differentiates gauss_means / gauss_stds only; som_vars is NOT differentiated here
+//   scenerf.py:533-536,473-481 ; scenerf.py:585-594   heads (sigmoid, softplus(x-1), relu(.)+c)
+//   resnetfc.py:133-164 ResnetFC;  utils.py:232-247  grid_sample(bilinear, zeros) w.r.t. the 5 feature maps
+//
+// Order: ray_backward_kernel (per ray: cotangents -> d raw MLP outputs of both passes)  ->  per chunk of points:
+// recompute the float32 forward keeping pre-activations, then the GEMM chain backwards (dX = dY W, dW += dY^T X,
+// db += colsum dY), then scatter d latent into the CHW feature-map gradients with atomics.
+// Parameter gradients are deterministic (no atomics, fixed chunk order); feature-map gradients use float atomicAdd.
+#include "kernels.cuh"
+
+namespace srf {
+
+constexpr int kBwdWarps = 4;
+constexpr int kMaxSB = 256;
+constexpr int kChunkB = 4096;
+
+struct RayBwdSmem {
+  float t[kMaxSB], z[kMaxSB], sg[kMaxSB], al[kMaxSB], T[kMaxSB], gw[kMaxSB], ga[kMaxSB], gtt[kMaxSB], gt[kMaxSB], gz[kMaxSB];
+};
+
+// one warp per ray
+template <int kMaxG>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+ray_backward_kernel(const __grid_constant__ DevParams p, int R, const float* __restrict__ raw,      // (R*S,4) main MLP output
+                    const float* __restrict__ t_sorted, const float* __restrict__ unit, const float* __restrict__ gauss_raw,
+                    const float* __restrict__ noise_n, srf_outputs fwd, srf_outputs cot,
+                    float* __restrict__ graw_main,      // (R*S,4)
+                    float* __restrict__ graw_gauss) {   // (R*G,2)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RayBwdSmem& sm = reinterpret_cast<RayBwdSmem*>(smem_raw)[threadIdx.x >> 5];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kBwdWarps + warp;
+  if (r >= R) return;
+  const int S = p.S, G = p.G, P = p.P;
+  const size_t base = (size_t)r * S;
+  const float uz = unit[r * 3 + 2];
+
+  for (int j = lane; j < S; j += 32) {
+    sm.t[j] = fmaxf(t_sorted[base + j], 0.0f);
+    sm.z[j] = fwd.depth_volumes[base + j];
+    sm.sg[j] = fwd.densities[base + j];
+    sm.al[j] = fwd.alphas[base + j];
+  }
+  __syncwarp();
+  // transmittance before each sample (same segment scan as the forward kernel)
+  const int spt = (S + 31) >> 5;
+  const int j0 = min(S, lane * spt), j1 = min(S, j0 + spt);
+  float seg = 1.0f;
+  for (int j = j0; j < j1; ++j) seg *= fadd(fsub(1.0f, sm.al[j]), 1e-10f);
+  float incl = seg;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= v;
+  }
+  float Tacc = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) Tacc = 1.0f;
+  for (int j = j0; j < j1; ++j) { sm.T[j] = Tacc; Tacc *= fadd(fsub(1.0f, sm.al[j]), 1e-10f); }
+  __syncwarp();
+  // arg-min sample of |depth - z| (scenerf.py:730-735), first index wins
+  const float depth = fwd.depth[r];
+  float best = __int_as_float(0x7f800000);
+  int best_j = 0x7fffffff;
+  for (int j = lane; j < S; j += 32) {
+    const float d = fabsf(fsub(depth, sm.z[j]));
+    if (d < best) { best = d; best_j = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+    if (ob < best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+  }
+  const float dz_star = fsub(depth, sm.z[best_j]);
+  const float sgn = (dz_star > 0.f) ? 1.f : ((dz_star < 0.f) ? -1.f : 0.f);
+  const float c_closest = cot.closest_pts_to_depths ? cot.closest_pts_to_depths[r] : 0.f;
+  const float c_wad = cot.weights_at_depth ? cot.weights_at_depth[r] : 0.f;
+  const float gd = (cot.depth ? cot.depth[r] : 0.f) + sgn * c_closest;
+  float cc[3] = {0.f, 0.f, 0.f};
+  if (cot.color) { cc[0] = cot.color[r * 3]; cc[1] = cot.color[r * 3 + 1]; cc[2] = cot.color[r * 3 + 2]; }
+
+  for (int j = lane; j < S; j += 32) {
+    const float4 o = reinterpret_cast<const float4*>(raw)[base + j];
+    const float c0 = sigmoidf_ref(o.x), c1 = sigmoidf_ref(o.y), c2 = sigmoidf_ref(o.z);
+    const float w = fwd.weights[base + j];
+    float gw = (cot.weights ? cot.weights[base + j] : 0.f) + gd * sm.z[j] + cc[0] * c0 + cc[1] * c1 + cc[2] * c2;
+    float gz = (cot.depth_volumes ? cot.depth_volumes[base + j] : 0.f) + gd * w;
+    if (j == best_j) { gw += c_wad; gz -= sgn * c_closest; }
+    sm.gw[j] = gw;
+    sm.gz[j] = gz;
+    sm.ga[j] = (cot.alphas ? cot.alphas[base + j] : 0.f) + gw * sm.T[j];
+    sm.gtt[j] = gw * sm.al[j] * sm.T[j];
+    // colour head: d sigmoid
+    float4 g;
+    g.x = cc[0] * w * c0 * (1.f - c0);
+    g.y = cc[1] * w * c1 * (1.f - c1);
+    g.z = cc[2] * w * c2 * (1.f - c2);
+    g.w = 0.f;
+    reinterpret_cast<float4*>(graw_main)[base + j] = g;
+  }
+  __syncwarp();
+  // suffix_k = sum_{j>k} gtt_j   (cumprod backward); ga_k -= suffix_k / s_k
+  float segsum = 0.f;
+  for (int j = j0; j < j1; ++j) segsum += sm.gtt[j];
+  float incl_r = segsum;                         // inclusive scan from the right over lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_down_sync(0xffffffffu, incl_r, o);
+    if (lane + o < 32) incl_r += v;
+  }
+  float suffix = __shfl_down_sync(0xffffffffu, incl_r, 1);
+  if (lane == 31) suffix = 0.f;
+  for (int j = j1 - 1; j >= j0; --j) {
+    sm.ga[j] -= suffix / fadd(fsub(1.0f, sm.al[j]), 1e-10f);
+    suffix += sm.gtt[j];
+  }
+  __syncwarp();
+  // alpha = 1 - exp(-delta*sigma)
+  for (int j = lane; j < S; j += 32) {
+    const float delta = (j == 0) ? sm.t[0] : fsub(sm.t[j], sm.t[j - 1]);
+    const float E = expf(-fmul(delta, sm.sg[j]));
+    const float ga = sm.ga[j];
+    sm.gtt[j] = ga * sm.sg[j] * E;               // reuse: g_delta
+    const float gsig = (cot.densities ? cot.densities[base + j] : 0.f) + ga * delta * E;
+    const float x3 = fsub(raw[(base + j) * 4 + 3], 1.0f);
+    const float dsoft = (x3 > 20.0f) ? 1.0f : fdiv(1.0f, fadd(1.0f, expf(-x3)));
+    graw_main[(base + j) * 4 + 3] = gsig * dsoft;
+  }
+  __syncwarp();
+  for (int j = lane; j < S; j += 32) {
+    float gt = sm.gtt[j] - ((j + 1 < S) ? sm.gtt[j + 1] : 0.f);
+    if (t_sorted[base + j] < 0.f) gt = 0.f;      // scenerf.py:707 (never active: samples are >= 0.1)
+    sm.gt[j] = gt + sm.gz[j] * uz;               // depth_volume = t * unit_z (utils.py:216)
+  }
+  __syncwarp();
+  // route to the gaussian that produced each sample (utils.py:204-214)
+  float gm[kMaxG], gs[kMaxG];
+#pragma unroll
+  for (int g = 0; g < kMaxG; ++g) { gm[g] = 0.f; gs[g] = 0.f; }
+  for (int i = lane; i < G * P; i += 32) {
+    const int g = i / P;
+    const float m = fwd.gaussian_means[(size_t)r * G + g], s = fwd.gaussian_stds[(size_t)r * G + g];
+    const float e = noise_n ? noise_n[(size_t)r * G * P + i] : philox_normal(p.seed, (uint32_t)r, (uint32_t)i);
+    const float t = fadd(m, fmul(e, s));
+    if (t < 0.1f) continue;
+    int lo = 0, hi = S;                          // lower_bound of t in the sorted distances (same float as the forward wrote)
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.t[mid] < t) lo = mid + 1; else hi = mid; }
+    const float gt = (lo < S) ? sm.gt[lo] : 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxG; ++k) if (k == g) { gm[k] += gt; gs[k] += gt * e; }
+  }
+#pragma unroll
+  for (int g = 0; g < kMaxG; ++g) { gm[g] = warp_sum(gm[g]); gs[g] = warp_sum(gs[g]); }
+  if (lane == 0) {
+    const float c_kl = cot.loss_kl ? cot.loss_kl[r] : 0.f;
+    for (int g = 0; g < G; ++g) {
+      const size_t ig = (size_t)r * G + g;
+      const float m1 = fwd.gaussian_means[ig], s1 = fwd.gaussian_stds[ig];
+      const float m2 = fwd.som_means[ig], nv = fwd.som_vars[ig];
+      const float mean_diff = fabsf(fsub(m1, m2));
+      const float var_diff = fabsf(fsub(sqrtf(fmul(s1, s1)), sqrtf(nv)));
+      const bool mask = (mean_diff > 0.1f) && (var_diff > 0.1f) && (nv > 0.0f);
+      float s2 = sqrtf(nv);
+      if (s2 < 1.5f) s2 = 1.5f;
+      float g_mean = gm[0], g_std = gs[0];
+#pragma unroll
+      for (int k = 1; k < kMaxG; ++k) if (k == g) { g_mean = gm[k]; g_std = gs[k]; }
+      g_mean += cot.gaussian_means ? cot.gaussian_means[ig] : 0.f;
+      g_std += cot.gaussian_stds ? cot.gaussian_stds[ig] : 0.f;
+      if (mask) {
+        const float gk = c_kl / (float)G;
+        g_mean += gk * (m1 - m2) / (s2 * s2);
+        g_std += gk * (-(s2 / (s1 * s1)) / (s2 / s1 + 1e-8f) + s1 / (s2 * s2));
+      }
+      const float m0 = linspace_at(p.g_start, p.g_end, G, g);
+      const float o0 = gauss_raw[ig * 2 + 0], o1 = gauss_raw[ig * 2 + 1];
+      graw_gauss[ig * 2 + 0] = (fadd(m0, o0) > 0.f) ? g_mean : 0.f;
+      graw_gauss[ig * 2 + 1] = (fadd(o1, p.base_std) > 0.f) ? g_std : 0.f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// float32 GEMM family, 64x64x16 tiles, 4x4 outputs per thread.
+//   C[M x N] = epilogue( sum_k a(m,k) * b(k,n) )
+//   AT=false: A stored [M][K] (lda)   AT=true : A stored [K][M] (lda)
+//   BT=true : B stored [N][K] (ldb)   BT=false: B stored [K][N] (ldb)
+//   epilogue: v = acc (+bias[n]); if mask: v = mask[m][n] > 0 ? v : 0; if R: v += R[m][n]; if accumulate: v += C[m][n]
+template <bool AT, bool BT, bool RELU_A, bool RELU_B>
+__global__ void __launch_bounds__(256)
+gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* C, int ldc, int M, int N, int K,
+            const float* __restrict__ bias, const float* __restrict__ mask, int ldm, const float* R, int ldr, int accumulate) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = threadIdx.x + e * 256;
+      {
+        const int rr = AT ? (idx & 63) : (idx >> 4), kk = AT ? (idx >> 6) : (idx & 15);
+        const int gm = m0 + rr, gk = k0 + kk;
+        float a = 0.f;
+        if (gm < M && gk < K) a = AT ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+        if (RELU_A) a = fmaxf(a, 0.f);
+        As[kk][rr] = a;
+      }
+      {
+        const int rr = BT ? (idx >> 4) : (idx & 63), kk = BT ? (idx & 15) : (idx >> 6);
+        const int gn = n0 + rr, gk = k0 + kk;
+        float b = 0.f;
+        if (gn < N && gk < K) b = BT ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+        if (RELU_B) b = fmaxf(b, 0.f);
+        Bs[kk][rr] = b;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[gn];
+      if (mask) v = (mask[(size_t)gm * ldm + gn] > 0.f) ? v : 0.f;
+      if (R) v += R[(size_t)gm * ldr + gn];
+      if (accumulate) v += C[(size_t)gm * ldc + gn];
+      C[(size_t)gm * ldc + gn] = v;
+    }
+  }
+}
+
+struct GemmOpt {
+  const float* bias = nullptr;
+  const float* mask = nullptr; int ldm = 0;
+  const float* R = nullptr; int ldr = 0;
+  int accumulate = 0;
+};
+template <bool AT, bool BT, bool RA, bool RB>
+static void gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const GemmOpt& o,
+                 cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  gemm_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, o.bias, o.mask, o.ldm, o.R, o.ldr, o.accumulate);
+}
+
+// gb[n] += sum_m dY[m][n]   (deterministic: one warp per 32 columns... one thread per column, 8 row lanes, fixed tree)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ dY, int ld, int M, int N, float* __restrict__ gb) {
+  __shared__ float part[8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < N)
+    for (int m = rl; m < M; m += 8) s += dY[(size_t)m * ld + c];
+  part[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
+    gb[c] += t;
+  }
+}
+static void colsum(const float* dY, int ld, int M, int N, float* gb, cudaStream_t st) {
+  colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(dY, ld, M, N, gb);
+}
+
+// dh[m][c] = (h3[m][c] > 0) ? sum_o g[m][o] * Wout[o][c] : 0        (lin_out backward w.r.t. its input)
+__global__ void __launch_bounds__(256)
+lin_out_dx_kernel(const float* __restrict__ g, int d_out, const float* __restrict__ Wout, const float* __restrict__ h3,
+                  float* __restrict__ dh, int M) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * kHidden) return;
+  const int m = i / kHidden, c = i % kHidden;
+  float v = 0.f;
+  for (int o = 0; o < d_out; ++o) v = fmaf(g[(size_t)m * d_out + o], Wout[o * kHidden + c], v);
+  dh[i] = (h3[i] > 0.f) ? v : 0.f;
+}
+
+// feature-map gradient: grad_chw[s][c][pixel] += w_tap * dz[point][ch_off[s] + c]   (one warp per point)
+struct PyrGrad { float* chw[kScales]; };
+__global__ void __launch_bounds__(256)
+scatter_latent_kernel(const __grid_constant__ DevParams p, const float* __restrict__ pts, int n, int point0,
+                      const float* __restrict__ dZ, int ld, PyrGrad gp) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int gi = point0 + i;
+  int sx, sy;
+  point_to_sphere(p, pts[(size_t)gi * 3 + 0], pts[(size_t)gi * 3 + 1], pts[(size_t)gi * 3 + 2], sx, sy);
+  const float* row = dZ + (size_t)i * ld;
+#pragma unroll
+  for (int s = 0; s < kScales; ++s) {
+    const Taps t = scale_taps(p, s, sx, sy);
+    if (!t.any) continue;
+    const int C = p.C[s];
+    const size_t plane = (size_t)p.H[s] * p.W[s];
+    float* g = gp.chw[s];
+    for (int c = lane; c < C; c += 32) {
+      const float v = row[p.ch_off[s] + c];
+      if (v == 0.f) continue;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t.off[k] >= 0) atomicAdd(g + (size_t)c * plane + t.off[k] / C, t.w[k] * v);
+    }
+  }
+}
+
+static inline int xin_ld_b(int d_latent) { return ((d_latent + kDX + 31) / 32) * 32; }
+
+size_t mlp_backward_workspace_bytes(int d_latent, int n_points) {
+  const size_t m = (size_t)(n_points < kChunkB ? n_points : kChunkB);
+  return m * ((size_t)2 * xin_ld_b(d_latent) + 10 * kHidden) * sizeof(float) + 256;
+}
+
+// grads: same layout as the weights (accumulated into); pyramid grads CHW (accumulated into).  Returns launches or -1.
+int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, const srf_mlp_weights& gw, float* const* grad_pyr_chw,
+                                const float* pts, const float* viewdir, int n, int n_per, const float* g_raw, void* workspace,
+                                size_t ws_bytes, cudaStream_t st) {
+  if (ws_bytes < mlp_backward_workspace_bytes(p.d_latent, n)) return -1;
+  const int ld = xin_ld_b(p.d_latent), H = kHidden, DL = p.d_latent;
+  const size_t cap = (size_t)(n < kChunkB ? n : kChunkB);
+  float* X = reinterpret_cast<float*>(workspace);
+  float* dZ = X + cap * ld;
+  float* PRE[3]; float* NET[3];
+  float* q = dZ + cap * ld;
+  for (int b = 0; b < 3; ++b) { PRE[b] = q; q += cap * H; NET[b] = q; q += cap * H; }
+  float* H3 = q; q += cap * H;
+  float* dH = q; q += cap * H;
+  float* dN = q; q += cap * H;
+  float* dP = q; q += cap * H;
+  auto G = [](const float* c) { return const_cast<float*>(c); };
+  PyrGrad gp;
+  for (int s = 0; s < kScales; ++s) gp.chw[s] = grad_pyr_chw[s];
+  int launches = 0;
+  for (int p0 = 0; p0 < n; p0 += kChunkB) {
+    const int m = (n - p0) < kChunkB ? (n - p0) : kChunkB;
+    const float* g_out = g_raw + (size_t)p0 * w.d_out;
+    // ---- forward recompute, keeping pre-activations (resnetfc.py:133-164) ----
+    launch_build_xin(p, pts, viewdir, m, n_per, p0, X, ld, st);
+    GemmOpt o;
+    o = GemmOpt(); o.bias = w.lin_in_b;
+    gemm<false, true, false, false>(X + DL, ld, w.lin_in_w, kDX, PRE[0], H, m, H, kDX, o, st);                 // h0 = lin_in(x)
+    for (int b = 0; b < 3; ++b) {
+      o = GemmOpt(); o.bias = w.lin_z_b[b]; o.R = (b == 0) ? PRE[0] : H3; o.ldr = H;
+      gemm<false, true, false, false>(X, ld, w.lin_z_w[b], DL, PRE[b], H, m, H, DL, o, st);                    // pre = h + lin_z(z)
+      o = GemmOpt(); o.bias = w.fc0_b[b];
+      gemm<false, true, true, false>(PRE[b], H, w.fc0_w[b], H, NET[b], H, m, H, H, o, st);                     // net = fc_0(relu(pre))
+      o = GemmOpt(); o.bias = w.fc1_b[b]; o.R = PRE[b]; o.ldr = H;
+      gemm<false, true, true, false>(NET[b], H, w.fc1_w[b], H, H3, H, m, H, H, o, st);                         // h = pre + fc_1(relu(net))
+      launches += 3;
+    }
+    // ---- backward ----
+    o = GemmOpt(); o.accumulate = 1;
+    gemm<true, false, false, true>(g_out, w.d_out, H3, H, G(gw.lin_out_w), H, w.d_out, H, m, o, st);           // gW_out += g^T relu(h3)
+    colsum(g_out, w.d_out, m, w.d_out, G(gw.lin_out_b), st);
+    lin_out_dx_kernel<<<(m * H + 255) / 256, 256, 0, st>>>(g_out, w.d_out, w.lin_out_w, H3, dH, m);
+    launches += 5;
+    for (int b = 2; b >= 0; --b) {
+      o = GemmOpt(); o.accumulate = 1;
+      gemm<true, false, false, true>(dH, H, NET[b], H, G(gw.fc1_w[b]), H, H, H, m, o, st);                     // gW_fc1 += dh^T relu(net)
+      colsum(dH, H, m, H, G(gw.fc1_b[b]), st);
+      o = GemmOpt(); o.mask = NET[b]; o.ldm = H;
+      gemm<false, false, false, false>(dH, H, w.fc1_w[b], H, dN, H, m, H, H, o, st);                           // dnet = (dh W_fc1) * (net>0)
+      o = GemmOpt(); o.accumulate = 1;
+      gemm<true, false, false, true>(dN, H, PRE[b], H, G(gw.fc0_w[b]), H, H, H, m, o, st);                     // gW_fc0 += dnet^T relu(pre)
+      colsum(dN, H, m, H, G(gw.fc0_b[b]), st);
+      o = GemmOpt(); o.mask = PRE[b]; o.ldm = H; o.R = dH; o.ldr = H;
+      gemm<false, false, false, false>(dN, H, w.fc0_w[b], H, dP, H, m, H, H, o, st);                           // dpre = dh + (dnet W_fc0) * (pre>0)
+      o = GemmOpt(); o.accumulate = 1;
+      gemm<true, false, false, false>(dP, H, X, ld, G(gw.lin_z_w[b]), DL, H, DL, m, o, st);                    // gW_linz += dpre^T z
+      colsum(dP, H, m, H, G(gw.lin_z_b[b]), st);
+      o = GemmOpt(); o.accumulate = (b == 2) ? 0 : 1;
+      gemm<false, false, false, false>(dP, H, w.lin_z_w[b], DL, dZ, ld, m, DL, H, o, st);                      // dz (+)= dpre W_linz
+      float* tmp = dH; dH = dP; dP = tmp;                                                                      // dh <- dpre
+      launches += 8;
+    }
+    o = GemmOpt(); o.accumulate = 1;
+    gemm<true, false, false, false>(dH, H, X + DL, ld, G(gw.lin_in_w), kDX, H, kDX, m, o, st);                 // gW_in += dh^T x
+    colsum(dH, H, m, H, G(gw.lin_in_b), st);
+    scatter_latent_kernel<<<(m + 7) / 8, 256, 0, st>>>(p, pts, m, p0, dZ, ld, gp);
+    launches += 5;
+  }
+  return launches;
+}
+
+void launch_ray_backward(const DevParams& p, int R, const float* raw, const float* t_sorted, const float* unit,
+                         const float* gauss_raw, const float* noise_n, const srf_outputs& fwd, const srf_outputs& cot,
+                         float* graw_main, float* graw_gauss, cudaStream_t st) {
+  const int blocks = (R + kBwdWarps - 1) / kBwdWarps;
+  const size_t smem = kBwdWarps * sizeof(RayBwdSmem);
+  if (p.G <= 4) {
+    cudaFuncSetAttribute(ray_backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ray_backward_kernel<4><<<blocks, kBwdWarps * 32, smem, st>>>(p, R, raw, t_sorted, unit, gauss_raw, noise_n, fwd, cot, graw_main, graw_gauss);
+  } else {
+    cudaFuncSetAttribute(ray_backward_kernel<kMaxGaussians>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ray_backward_kernel<kMaxGaussians><<<blocks, kBwdWarps * 32, smem, st>>>(p, R, raw, t_sorted, unit, gauss_raw, noise_n, fwd, cot, graw_main, graw_gauss);
+  }
+}
+
+}  // namespace srf

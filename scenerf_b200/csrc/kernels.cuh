@@ -36,6 +36,19 @@ int run_point_mlp_simt(const DevParams& p, const srf_mlp_weights& w, const float
                        int n_per, float* raw_out, int32_t* dbg_sphere, void* workspace, size_t ws_bytes,
                        cudaStream_t st);
 
+// one warp per point: X[i] = [ gathered latent (d_latent) | positional encoding (39) | viewdir (3) | 0-pad ], row stride ld
+void launch_build_xin(const DevParams& p, const float* pts, const float* viewdir, int m, int n_per, int point0, float* X, int ld,
+                      cudaStream_t st);
+
+// backward.cu : float32 backward of the path (reference: torch.autograd through scenerf.py:392-748)
+size_t mlp_backward_workspace_bytes(int d_latent, int n_points);
+int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, const srf_mlp_weights& gw, float* const* grad_pyr_chw,
+                                const float* pts, const float* viewdir, int n, int n_per, const float* g_raw, void* workspace,
+                                size_t ws_bytes, cudaStream_t st);
+void launch_ray_backward(const DevParams& p, int R, const float* raw, const float* t_sorted, const float* unit,
+                         const float* gauss_raw, const float* noise_n, const srf_outputs& fwd, const srf_outputs& cot,
+                         float* graw_main, float* graw_gauss, cudaStream_t st);
+
 // mlp_tc.cu : tcgen05 tensor-core point MLP.
 size_t tc_weights_bytes(int d_out, int d_latent);
 int pack_weights_tc(const srf_mlp_weights& w, void* dst, size_t bytes, cudaStream_t st);

@@ -127,6 +127,11 @@ lin_out_kernel(const float* __restrict__ Hh, const float* __restrict__ W, const 
     for (int o = 0; o < d_out; ++o) out[(size_t)i * d_out + o] = acc[o] + bias[o];
 }
 
+void launch_build_xin(const DevParams& p, const float* pts, const float* viewdir, int m, int n_per, int point0, float* X, int ld,
+                      cudaStream_t st) {
+  build_xin_kernel<<<(m + 7) / 8, 256, 0, st>>>(p, pts, viewdir, m, n_per, point0, X, ld, nullptr);
+}
+
 size_t simt_workspace_bytes(int d_latent, int n_points) {
   const size_t chunk = (size_t)(n_points < kChunk ? n_points : kChunk);
   return chunk * ((size_t)xin_ld(d_latent) + 2 * kHidden) * sizeof(float) + 256;

@@ -9,12 +9,6 @@
 
 namespace srf {
 
-__device__ __forceinline__ float linspace_at(float start, float end, int steps, int i) {
-  // ATen linspace: lower half start + step*i, upper half end - step*(steps-1-i)
-  if (steps == 1) return start;
-  const float step = fdiv(fsub(end, start), (float)(steps - 1));
-  return (i < steps / 2) ? fadd(start, fmul(step, (float)i)) : fsub(end, fmul(step, (float)(steps - 1 - i)));
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void ray_setup_kernel(const __grid_constant__ DevParams p, const float* __restrict__ pixels, int R,
@@ -44,17 +38,6 @@ __global__ void ray_setup_kernel(const __grid_constant__ DevParams p, const floa
 constexpr int kWarpsPerBlock = 4;
 constexpr int kMaxS = 256;
 
-__device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t ray, uint32_t idx, uint32_t stream) {
-  const uint4 o = philox4x32(make_uint4(ray, idx >> 2, stream, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const uint32_t v[4] = {o.x, o.y, o.z, o.w};
-  return u01(v[idx & 3]);
-}
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t ray, uint32_t idx) {
-  const uint4 o = philox4x32(make_uint4(ray, idx >> 1, 2u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const float u1 = ((float)(((idx & 1) ? o.z : o.x) >> 8) + 1.0f) * (1.0f / 16777216.0f);   // (0,1]
-  const float u2 = u01((idx & 1) ? o.w : o.y);
-  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-}
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sample_sort_kernel(const __grid_constant__ DevParams p, int R, const float* __restrict__ unit,
@@ -134,14 +117,6 @@ sample_sort_kernel(const __grid_constant__ DevParams p, int R, const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-__device__ __forceinline__ float sigmoidf_ref(float x) { return fdiv(1.0f, fadd(1.0f, expf(-x))); }
-__device__ __forceinline__ float softplusf_ref(float x) { return (x > 20.0f) ? x : log1pf(expf(x)); }
 
 struct CompositeSmem {
   float t[kMaxS], dv[kMaxS], sg[kMaxS], al[kMaxS], w[kMaxS], c0[kMaxS], c1[kMaxS], c2[kMaxS];

@@ -311,6 +311,87 @@ def tsdf_fusion():
     return out
 
 
+GRAD_KEYS = ("depth", "color", "gaussian_means", "gaussian_stds", "weights_at_depth", "closest_pts_to_depths", "loss_kl",
+             "alphas", "densities", "weights", "depth_volumes")          # som_vars: see DESIGN.md (non-differentiable here)
+
+
+def cotangent(key_idx, shape):
+    n = int(np.prod(shape))
+    return synth.hash_normalish(900 + key_idx, n).reshape(shape).astype(np.float32)
+
+
+def grad_digest(name, G, out):
+    """Big gradient tensors are stored as projections: G@u, G.T@v (fixed pseudo-random u, v) and the strided block
+    G[::16, ::16]; small ones in full."""
+    G = np.ascontiguousarray(G, dtype=np.float32)
+    if G.ndim == 1 or G.size <= 65536:
+        out["g:" + name] = G
+        return
+    u = synth.hash_normalish(700, G.shape[1]).astype(np.float64)
+    v = synth.hash_normalish(701, G.shape[0]).astype(np.float64)
+    out["gu:" + name] = (G.astype(np.float64) @ u).astype(np.float32)
+    out["gv:" + name] = (G.astype(np.float64).T @ v).astype(np.float32)
+    out["gs:" + name] = G[::16, ::16].copy()
+
+
+def run_grad_case(cfg, pixels, pyr_seed):
+    """Reference autograd through render_rays_batch: L = sum_k <out_k, C_k> with fixed cotangents C_k; gradients w.r.t.
+    the 2 x 22 MLP parameter tensors, the 5 pyramid tensors and the raw MLP outputs."""
+    model = build_reference_model(cfg)
+    for p_ in model.parameters():
+        p_.requires_grad_(True)
+    x_rgb = {k: torch.from_numpy(v).requires_grad_(True) for k, v in synth.make_pyramid(pyr_seed, cfg.sphere_W, cfg.sphere_H).items()}
+    raws = {}
+    def keep(tag):
+        def hook(m, i, o):
+            o.retain_grad()
+            raws[tag] = o
+        return hook
+    model.mlp.register_forward_hook(keep("main"))
+    model.mlp_gaussian.register_forward_hook(keep("gauss"))
+    K, T, pix = torch.from_numpy(cfg.K), torch.from_numpy(cfg.T), torch.from_numpy(pixels)
+    torch.manual_seed(0)
+    with _Recorder(model) as r:
+        if cfg.dataset == "kitti":
+            out = model.render_rays_batch(K, T, x_rgb, ray_batch_size=pix.shape[0], sampled_pixels=pix)
+        else:
+            out = model.render_rays_batch(K, T, x_rgb, sampled_pixels=pix, ray_batch_size=pix.shape[0])
+    L = 0
+    for i, k in enumerate(GRAD_KEYS):
+        L = L + (out[k] * torch.from_numpy(cotangent(i, tuple(out[k].shape)))).sum()
+    L.backward()
+    R = pix.shape[0]
+    g = {k: v.detach().numpy() for k, v in out.items()}
+    g["noise_u"] = r.rec["noise_u"][0].reshape(R, -1).numpy()
+    g["noise_n"] = r.rec["noise_n"][0].reshape(R, -1).numpy()
+    g["pixels"] = pixels
+    g["loss"] = np.float64(L.item())
+    g["graw_main"] = raws["main"].grad.reshape(-1, 4).numpy()
+    g["graw_gauss"] = raws["gauss"].grad.reshape(-1, 2).numpy()
+    for tag, net in (("main", model.mlp), ("gauss", model.mlp_gaussian)):
+        for name, p_ in net.named_parameters():
+            grad_digest("%s.%s" % (tag, name), p_.grad.numpy(), g)
+    for k, t in x_rgb.items():
+        G = t.grad.numpy()
+        g["gpyr_chsum:" + k] = G.sum(axis=(1, 2), dtype=np.float64).astype(np.float32)
+        g["gpyr_pixsum:" + k] = G.sum(axis=0, dtype=np.float64).astype(np.float32)
+        g["gpyr_head:" + k] = G[:4].copy()
+        g["gpyr_abs:" + k] = np.float64(np.abs(G).sum(dtype=np.float64))
+    return g
+
+
+@case
+def grad_kitti():
+    cfg = synth.config_A(name="grad_kitti", sphere_W=300, sphere_H=90, yaw_deg=10.0, tz=1.0)
+    return run_grad_case(cfg, synth.random_pixels(23, 48, cfg.img_W, cfg.img_H), pyr_seed=41)
+
+
+@case
+def grad_bf():
+    cfg = synth.config_C(name="grad_bf", sphere_W=160, sphere_H=120, n_pts_uni=32)
+    return run_grad_case(cfg, synth.random_pixels(24, 40, cfg.img_W, cfg.img_H), pyr_seed=42)
+
+
 def sweep_setup():
     """Small-image stand-in of generate_novel_depths.py: 244x74 image (KITTI intrinsics / 5), stride-4 grid (61x19 rays),
     the 6 poses of sample_rel_poses(step=1.0, angle=10, max_distance=1.1)."""
