@@ -291,13 +291,109 @@ def run_sweep(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def run_train(args, rank, world, local):
+    """--workload train: the backward row.  One step = what the reference's training does per source frame
+    (scenerf.py:243-320): render_rays_batch on 1200 random pixels of the stride-2 grid in ONE chunk (64 samples/ray, KITTI
+    defaults, sphere 1500x452), a depth + colour + KL loss, backward to the 2x22 ResnetFC tensors and the 5 feature maps.
+    float32 SIMT forward + backward (csrc/backward.cu).  Every rank runs its own frame (data parallel; the gradient
+    all-reduce stays PyTorch DDP's)."""
+    import time
+    import torch
+    import torch.distributed as dist
+    from scenerf_b200 import synth
+    from scenerf_b200.autograd import TrainableRenderer, PARAM_KEYS
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = synth.config_A(name="train")
+    R = args.rays if args.rays > 0 else 1200
+    pm, pg = synth.make_model_params(cfg)
+    mk = lambda d: {k: torch.from_numpy(d[k]).to(dev).requires_grad_(True) for k in PARAM_KEYS}
+    tm, tg = mk(pm), mk(pg)
+    x_rgb = {k: torch.from_numpy(v).to(dev).requires_grad_(True) for k, v in synth.make_pyramid(5 + rank, cfg.sphere_W, cfg.sphere_H).items()}
+    t = TrainableRenderer(hp_from_cfg(cfg), tm, tg, device=dev, rng="philox")
+    K, T = torch.from_numpy(cfg.K).to(dev), torch.from_numpy(cfg.T).to(dev)
+    grid = synth.grid_pixels(cfg.img_W, cfg.img_H, stride=2)
+    sel = np.random.default_rng(7 + rank).permutation(grid.shape[0])[:R]
+    pix_host = torch.from_numpy(np.ascontiguousarray(grid[sel])).pin_memory()
+    target = torch.rand(R, 3, device=dev)
+
+    def step():
+        for p_ in list(tm.values()) + list(tg.values()) + list(x_rgb.values()):
+            p_.grad = None
+        out = t.render_rays_batch(K, T, x_rgb, sampled_pixels=pix_host.to(dev, non_blocking=True), ray_batch_size=R)
+        loss = (out["color"] - target).abs().mean() + 0.01 * out["depth"].mean() + out["loss_kl"].mean() \
+            + 0.01 * (out["gaussian_means"] - out["depth"].detach().unsqueeze(-1)).abs().min(dim=1)[0].mean()
+        loss.backward()
+        return loss
+
+    for _ in range(args.warmup):
+        loss = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e[0].record()
+    for _ in range(args.steps):
+        loss = step()
+        lv = float(loss.detach().cpu())                       # D2H read of the step's result
+    e[1].record()
+    torch.cuda.synchronize()
+    ms = e[0].elapsed_time(e[1]) / args.steps
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    # forward / backward split (CUDA events around the two halves of one more step)
+    for p_ in list(tm.values()) + list(tg.values()) + list(x_rgb.values()):
+        p_.grad = None
+    e[2].record()
+    out = t.render_rays_batch(K, T, x_rgb, sampled_pixels=pix_host.to(dev), ray_batch_size=R)
+    loss = (out["color"] - target).abs().mean() + 0.01 * out["depth"].mean() + out["loss_kl"].mean()
+    e[3].record()
+    loss.backward()
+    e[0].record()
+    torch.cuda.synchronize()
+    fwd_ms, bwd_ms = e[2].elapsed_time(e[3]), e[3].elapsed_time(e[0])
+    flop_fwd = R * flop_per_ray(cfg)
+    flop_step = 4.0 * flop_fwd          # forward + recompute + dX GEMMs + dW GEMMs, each = one forward's FLOPs
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # 148 SMs x 128 FMA lanes x 2 x max clock
+    res = {"metric": "training rays/sec (render_rays_batch forward + backward, %d rays x %d samples per step)" % (R, cfg.S),
+           "value": world * R / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "dtype": "f32", "data": "synthetic", "scaling": "weak", "higher_is_better": True,
+           "forward_ms": fwd_ms, "backward_ms": bwd_ms, "loss": lv,
+           "gpu_launches": int(t.renderer.last_launches + t.renderer.last_backward_launches),
+           "roofline": {"bound": "fp32 FMA (SIMT)", "achieved": flop_step / (ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                        "frac": flop_step / (ms * 1e-3) / 1e12 / fp32_peak,
+                        "executed_flop_per_step": flop_step, "algorithmic_flop_per_step": 3.0 * flop_fwd,
+                        "note": "peak = 148 SMs x 128 lanes x 2 FLOP x 1.965 GHz; the backward recomputes the forward per 4096-point chunk"}}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import scenerf_oracle as so, backward_oracle as bo
+        n = 24
+        orc = so.OracleRenderer(cfg, pm, pg)
+        pyr = synth.make_pyramid(5, cfg.sphere_W, cfg.sphere_H)
+        rng = np.random.default_rng(0)
+        nu, nn_ = rng.random((n, cfg.n_pts_uni)).astype(np.float32), rng.standard_normal((n, cfg.n_gaussians * cfg.n_pts_per_gaussian)).astype(np.float32)
+        cot = {"depth": np.full(n, 0.01 / n), "color": np.full((n, 3), 1.0 / (3 * n)), "loss_kl": np.full(n, 1.0 / n)}
+        t0 = time.perf_counter()
+        bo.render_backward(orc, cfg.K, cfg.T, pyr, grid[sel][:n], nu, nn_, cot)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": n / dt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "%d rays x %d samples forward + backward with the numpy oracle (BLAS threads), %.1f s" % (n, cfg.S, dt)}
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="B", choices=["A", "B", "C", "sweep"])
+    ap.add_argument("--workload", default="B", choices=["A", "B", "C", "sweep", "train"])
     ap.add_argument("--sweep-poses", type=int, default=63)
     ap.add_argument("--sweep-scale", type=int, default=2)
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
@@ -312,6 +408,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload == "sweep":
         run_sweep(args, rank, world, local_rank)
+        return
+    if args.workload == "train":
+        run_train(args, rank, world, local_rank)
         return
     if args.impl == "reference":
         run_reference(args, rank, world)

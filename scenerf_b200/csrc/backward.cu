@@ -20,7 +20,8 @@ namespace srf {
 
 constexpr int kBwdWarps = 4;
 constexpr int kMaxSB = 256;
-constexpr int kChunkB = 4096;
+constexpr int kChunkB = 9472;                  // 74 row tiles of 128 x 4 column tiles of the 512-wide GEMMs = 296 CTAs = 148 SMs x 2
+constexpr size_t kSplitKFloats = (size_t)4 * 512 * 2528;     // split-K scratch of the weight-gradient GEMMs (20 MB)
 
 struct RayBwdSmem {
   float t[kMaxSB], z[kMaxSB], sg[kMaxSB], al[kMaxSB], T[kMaxSB], gw[kMaxSB], ga[kMaxSB], gtt[kMaxSB], gt[kMaxSB], gz[kMaxSB];
@@ -189,83 +190,22 @@ ray_backward_kernel(const __grid_constant__ DevParams p, int R, const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// float32 GEMM family, 64x64x16 tiles, 4x4 outputs per thread.
-//   C[M x N] = epilogue( sum_k a(m,k) * b(k,n) )
-//   AT=false: A stored [M][K] (lda)   AT=true : A stored [K][M] (lda)
-//   BT=true : B stored [N][K] (ldb)   BT=false: B stored [K][N] (ldb)
-//   epilogue: v = acc (+bias[n]); if mask: v = mask[m][n] > 0 ? v : 0; if R: v += R[m][n]; if accumulate: v += C[m][n]
-template <bool AT, bool BT, bool RELU_A, bool RELU_B>
-__global__ void __launch_bounds__(256)
-gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* C, int ldc, int M, int N, int K,
-            const float* __restrict__ bias, const float* __restrict__ mask, int ldm, const float* R, int ldr, int accumulate) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = threadIdx.x + e * 256;
-      {
-        const int rr = AT ? (idx & 63) : (idx >> 4), kk = AT ? (idx >> 6) : (idx & 15);
-        const int gm = m0 + rr, gk = k0 + kk;
-        float a = 0.f;
-        if (gm < M && gk < K) a = AT ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
-        if (RELU_A) a = fmaxf(a, 0.f);
-        As[kk][rr] = a;
-      }
-      {
-        const int rr = BT ? (idx >> 4) : (idx & 63), kk = BT ? (idx & 15) : (idx >> 6);
-        const int gn = n0 + rr, gk = k0 + kk;
-        float b = 0.f;
-        if (gn < N && gk < K) b = BT ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
-        if (RELU_B) b = fmaxf(b, 0.f);
-        Bs[kk][rr] = b;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + ty * 4 + i;
-    if (gm >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gn = n0 + tx * 4 + j;
-      if (gn >= N) continue;
-      float v = acc[i][j];
-      if (bias) v += bias[gn];
-      if (mask) v = (mask[(size_t)gm * ldm + gn] > 0.f) ? v : 0.f;
-      if (R) v += R[(size_t)gm * ldr + gn];
-      if (accumulate) v += C[(size_t)gm * ldc + gn];
-      C[(size_t)gm * ldc + gn] = v;
-    }
-  }
-}
-
 struct GemmOpt {
   const float* bias = nullptr;
   const float* mask = nullptr; int ldm = 0;
   const float* R = nullptr; int ldr = 0;
   int accumulate = 0;
+  float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
 };
 template <bool AT, bool BT, bool RA, bool RB>
 static void gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const GemmOpt& o,
                  cudaStream_t st) {
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  gemm_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, o.bias, o.mask, o.ldm, o.R, o.ldr, o.accumulate);
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.at = AT; g.relu_a = RA; g.B = B; g.ldb = ldb; g.bt = BT; g.relu_b = RB;
+  g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  g.bias = o.bias; g.mask = o.mask; g.ldm = o.ldm; g.R = o.R; g.ldr = o.ldr; g.accumulate = o.accumulate;
+  g.splitk_ws = o.splitk_ws; g.splitk_ws_floats = o.splitk_ws_floats;
+  launch_gemm(g, st);
 }
 
 // gb[n] += sum_m dY[m][n]   (deterministic: one warp per 32 columns... one thread per column, 8 row lanes, fixed tree)
@@ -334,7 +274,7 @@ static inline int xin_ld_b(int d_latent) { return ((d_latent + kDX + 31) / 32) *
 
 size_t mlp_backward_workspace_bytes(int d_latent, int n_points) {
   const size_t m = (size_t)(n_points < kChunkB ? n_points : kChunkB);
-  return m * ((size_t)2 * xin_ld_b(d_latent) + 10 * kHidden) * sizeof(float) + 256;
+  return m * ((size_t)2 * xin_ld_b(d_latent) + 10 * kHidden) * sizeof(float) + kSplitKFloats * sizeof(float) + 256;
 }
 
 // grads: same layout as the weights (accumulated into); pyramid grads CHW (accumulated into).  Returns launches or -1.
@@ -353,6 +293,7 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
   float* dH = q; q += cap * H;
   float* dN = q; q += cap * H;
   float* dP = q; q += cap * H;
+  float* SK = q;
   auto G = [](const float* c) { return const_cast<float*>(c); };
   PyrGrad gp;
   for (int s = 0; s < kScales; ++s) gp.chw[s] = grad_pyr_chw[s];
@@ -375,23 +316,23 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
       launches += 3;
     }
     // ---- backward ----
-    o = GemmOpt(); o.accumulate = 1;
+    o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
     gemm<true, false, false, true>(g_out, w.d_out, H3, H, G(gw.lin_out_w), H, w.d_out, H, m, o, st);           // gW_out += g^T relu(h3)
     colsum(g_out, w.d_out, m, w.d_out, G(gw.lin_out_b), st);
     lin_out_dx_kernel<<<(m * H + 255) / 256, 256, 0, st>>>(g_out, w.d_out, w.lin_out_w, H3, dH, m);
     launches += 5;
     for (int b = 2; b >= 0; --b) {
-      o = GemmOpt(); o.accumulate = 1;
+      o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
       gemm<true, false, false, true>(dH, H, NET[b], H, G(gw.fc1_w[b]), H, H, H, m, o, st);                     // gW_fc1 += dh^T relu(net)
       colsum(dH, H, m, H, G(gw.fc1_b[b]), st);
       o = GemmOpt(); o.mask = NET[b]; o.ldm = H;
       gemm<false, false, false, false>(dH, H, w.fc1_w[b], H, dN, H, m, H, H, o, st);                           // dnet = (dh W_fc1) * (net>0)
-      o = GemmOpt(); o.accumulate = 1;
+      o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
       gemm<true, false, false, true>(dN, H, PRE[b], H, G(gw.fc0_w[b]), H, H, H, m, o, st);                     // gW_fc0 += dnet^T relu(pre)
       colsum(dN, H, m, H, G(gw.fc0_b[b]), st);
       o = GemmOpt(); o.mask = PRE[b]; o.ldm = H; o.R = dH; o.ldr = H;
       gemm<false, false, false, false>(dN, H, w.fc0_w[b], H, dP, H, m, H, H, o, st);                           // dpre = dh + (dnet W_fc0) * (pre>0)
-      o = GemmOpt(); o.accumulate = 1;
+      o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
       gemm<true, false, false, false>(dP, H, X, ld, G(gw.lin_z_w[b]), DL, H, DL, m, o, st);                    // gW_linz += dpre^T z
       colsum(dP, H, m, H, G(gw.lin_z_b[b]), st);
       o = GemmOpt(); o.accumulate = (b == 2) ? 0 : 1;
@@ -399,7 +340,7 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
       float* tmp = dH; dH = dP; dP = tmp;                                                                      // dh <- dpre
       launches += 8;
     }
-    o = GemmOpt(); o.accumulate = 1;
+    o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
     gemm<true, false, false, false>(dH, H, X + DL, ld, G(gw.lin_in_w), kDX, H, kDX, m, o, st);                 // gW_in += dh^T x
     colsum(dH, H, m, H, G(gw.lin_in_b), st);
     scatter_latent_kernel<<<(m + 7) / 8, 256, 0, st>>>(p, pts, m, p0, dZ, ld, gp);

@@ -36,6 +36,16 @@ int run_point_mlp_simt(const DevParams& p, const srf_mlp_weights& w, const float
                        int n_per, float* raw_out, int32_t* dbg_sphere, void* workspace, size_t ws_bytes,
                        cudaStream_t st);
 
+// gemm.cu : float32 SIMT GEMM (see the file header for operand layouts and the epilogue)
+struct GemmArgs {
+  const float* A = nullptr; int lda = 0; bool at = false; bool relu_a = false;
+  const float* B = nullptr; int ldb = 0; bool bt = false; bool relu_b = false;
+  float* C = nullptr; int ldc = 0; int M = 0, N = 0, K = 0;
+  const float* bias = nullptr; const float* mask = nullptr; int ldm = 0; const float* R = nullptr; int ldr = 0; int accumulate = 0;
+  float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;   // optional scratch: enables deterministic split-K for long-K, few-tile shapes
+};
+int launch_gemm(const GemmArgs& g, cudaStream_t st);    // 0, or -1 for an operand-layout combination that is not instantiated
+
 // one warp per point: X[i] = [ gathered latent (d_latent) | positional encoding (39) | viewdir (3) | 0-pad ], row stride ld
 void launch_build_xin(const DevParams& p, const float* pts, const float* viewdir, int m, int n_per, int point0, float* X, int ld,
                       cudaStream_t st);

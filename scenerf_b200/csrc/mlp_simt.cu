@@ -9,7 +9,7 @@
 
 namespace srf {
 
-constexpr int kChunk = 8192;                  // points per pass (x_in chunk = 8192 x 2528 fp32 = 83 MB)
+constexpr int kChunk = 9472;                  // points per pass: 74 row tiles x 4 column tiles = 296 CTAs = 148 SMs x 2 (x_in chunk 96 MB)
 
 static inline int xin_ld(int d_latent) { return ((d_latent + kDX + 31) / 32) * 32; }
 
@@ -52,58 +52,6 @@ build_xin_kernel(const __grid_constant__ DevParams p, const float* __restrict__ 
   }
 }
 
-// C[M x N] = (accumulate ? C : 0) + ( relu?(A)[M x K] * W[N x K]^T + bias ),  all fp32, 64x64x16 tiles, 4x4 per thread
-template <bool kRelu>
-__global__ void __launch_bounds__(256)
-sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-                const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K,
-                int accumulate) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Ws[16][64 + 4];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    // 64 rows x 16 k : 1024 elements, 256 threads x 4
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = threadIdx.x + e * 256;
-      const int rr = idx >> 4, kk = idx & 15;
-      const int gm = m0 + rr, gk = k0 + kk;
-      float a = (gm < M && gk < K) ? A[(size_t)gm * lda + gk] : 0.0f;
-      if (kRelu) a = fmaxf(a, 0.0f);
-      As[kk][rr] = a;
-      const int gn = n0 + rr;
-      Ws[kk][rr] = (gn < N && gk < K) ? W[(size_t)gn * ldw + gk] : 0.0f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Ws[kk][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + ty * 4 + i;
-    if (gm >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gn = n0 + tx * 4 + j;
-      if (gn >= N) continue;
-      float v = acc[i][j] + bias[gn];
-      if (accumulate) v = C[(size_t)gm * ldc + gn] + v;
-      C[(size_t)gm * ldc + gn] = v;
-    }
-  }
-}
-
 // lin_out: N = d_out (2 or 4) outputs per row, K = 512: one warp per row.
 __global__ void __launch_bounds__(256)
 lin_out_kernel(const float* __restrict__ Hh, const float* __restrict__ W, const float* __restrict__ bias,
@@ -137,11 +85,14 @@ size_t simt_workspace_bytes(int d_latent, int n_points) {
   return chunk * ((size_t)xin_ld(d_latent) + 2 * kHidden) * sizeof(float) + 256;
 }
 
+// C[M x N] = (accumulate ? C : 0) + ( relu?(A)[M x K] * W[N x K]^T + bias )   (gemm.cu)
 template <bool kRelu>
 static void gemm(const float* A, int lda, const float* W, int ldw, const float* b, float* C, int M, int N, int K,
                  int accumulate, cudaStream_t st) {
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  sgemm_nt_kernel<kRelu><<<grid, 256, 0, st>>>(A, lda, W, ldw, b, C, N, M, N, K, accumulate);
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.relu_a = kRelu; g.B = W; g.ldb = ldw; g.bt = true; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K;
+  g.bias = b; g.accumulate = accumulate;
+  launch_gemm(g, st);
 }
 
 int run_point_mlp_simt(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n,

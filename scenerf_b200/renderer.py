@@ -102,6 +102,7 @@ class B200Renderer:
         self._ws = None
         self.seed = 0x5CE9E2F
         self.last_launches = 0
+        self.last_backward_launches = 0
 
     # ------------------------------------------------------------------------------------------------------------
     @classmethod
