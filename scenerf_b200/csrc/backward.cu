@@ -208,25 +208,37 @@ static void gemm(const float* A, int lda, const float* B, int ldb, float* C, int
   launch_gemm(g, st);
 }
 
-// gb[n] += sum_m dY[m][n]   (deterministic: one warp per 32 columns... one thread per column, 8 row lanes, fixed tree)
+// gb[n] += sum_m dY[m][n], deterministic two-stage: kColSegs row segments (grid.y) -> part[seg][n], then a fixed-order sum
+constexpr int kColSegs = 64;
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ dY, int ld, int M, int N, float* __restrict__ gb) {
-  __shared__ float part[8][32];
+colsum_partial_kernel(const float* __restrict__ dY, int ld, int M, int N, float* __restrict__ part) {
+  __shared__ float sh[8][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  const int rows_per = (M + kColSegs - 1) / kColSegs;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
   float s = 0.f;
   if (c < N)
-    for (int m = rl; m < M; m += 8) s += dY[(size_t)m * ld + c];
-  part[rl][threadIdx.x & 31] = s;
+    for (int m = r0 + rl; m < r1; m += 8) s += dY[(size_t)m * ld + c];
+  sh[rl][threadIdx.x & 31] = s;
   __syncthreads();
   if (rl == 0 && c < N) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x & 31];
-    gb[c] += t;
+    for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x & 31];
+    part[(size_t)blockIdx.y * N + c] = t;
   }
 }
-static void colsum(const float* dY, int ld, int M, int N, float* gb, cudaStream_t st) {
-  colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(dY, ld, M, N, gb);
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ part, int N, float* __restrict__ gb) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float t = 0.f;
+  for (int s = 0; s < kColSegs; ++s) t += part[(size_t)s * N + c];
+  gb[c] += t;
+}
+static void colsum(const float* dY, int ld, int M, int N, float* gb, float* scratch, cudaStream_t st) {
+  colsum_partial_kernel<<<dim3((N + 31) / 32, kColSegs), 256, 0, st>>>(dY, ld, M, N, scratch);
+  colsum_final_kernel<<<(N + 255) / 256, 256, 0, st>>>(scratch, N, gb);
 }
 
 // dh[m][c] = (h3[m][c] > 0) ? sum_o g[m][o] * Wout[o][c] : 0        (lin_out backward w.r.t. its input)
@@ -318,23 +330,23 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
     // ---- backward ----
     o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
     gemm<true, false, false, true>(g_out, w.d_out, H3, H, G(gw.lin_out_w), H, w.d_out, H, m, o, st);           // gW_out += g^T relu(h3)
-    colsum(g_out, w.d_out, m, w.d_out, G(gw.lin_out_b), st);
+    colsum(g_out, w.d_out, m, w.d_out, G(gw.lin_out_b), SK, st);
     lin_out_dx_kernel<<<(m * H + 255) / 256, 256, 0, st>>>(g_out, w.d_out, w.lin_out_w, H3, dH, m);
     launches += 5;
     for (int b = 2; b >= 0; --b) {
       o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
       gemm<true, false, false, true>(dH, H, NET[b], H, G(gw.fc1_w[b]), H, H, H, m, o, st);                     // gW_fc1 += dh^T relu(net)
-      colsum(dH, H, m, H, G(gw.fc1_b[b]), st);
+      colsum(dH, H, m, H, G(gw.fc1_b[b]), SK, st);
       o = GemmOpt(); o.mask = NET[b]; o.ldm = H;
       gemm<false, false, false, false>(dH, H, w.fc1_w[b], H, dN, H, m, H, H, o, st);                           // dnet = (dh W_fc1) * (net>0)
       o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
       gemm<true, false, false, true>(dN, H, PRE[b], H, G(gw.fc0_w[b]), H, H, H, m, o, st);                     // gW_fc0 += dnet^T relu(pre)
-      colsum(dN, H, m, H, G(gw.fc0_b[b]), st);
+      colsum(dN, H, m, H, G(gw.fc0_b[b]), SK, st);
       o = GemmOpt(); o.mask = PRE[b]; o.ldm = H; o.R = dH; o.ldr = H;
       gemm<false, false, false, false>(dN, H, w.fc0_w[b], H, dP, H, m, H, H, o, st);                           // dpre = dh + (dnet W_fc0) * (pre>0)
       o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
       gemm<true, false, false, false>(dP, H, X, ld, G(gw.lin_z_w[b]), DL, H, DL, m, o, st);                    // gW_linz += dpre^T z
-      colsum(dP, H, m, H, G(gw.lin_z_b[b]), st);
+      colsum(dP, H, m, H, G(gw.lin_z_b[b]), SK, st);
       o = GemmOpt(); o.accumulate = (b == 2) ? 0 : 1;
       gemm<false, false, false, false>(dP, H, w.lin_z_w[b], DL, dZ, ld, m, DL, H, o, st);                      // dz (+)= dpre W_linz
       float* tmp = dH; dH = dP; dP = tmp;                                                                      // dh <- dpre
@@ -342,7 +354,7 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
     }
     o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
     gemm<true, false, false, false>(dH, H, X + DL, ld, G(gw.lin_in_w), kDX, H, kDX, m, o, st);                 // gW_in += dh^T x
-    colsum(dH, H, m, H, G(gw.lin_in_b), st);
+    colsum(dH, H, m, H, G(gw.lin_in_b), SK, st);
     scatter_latent_kernel<<<(m + 7) / 8, 256, 0, st>>>(p, pts, m, p0, dZ, ld, gp);
     launches += 5;
   }

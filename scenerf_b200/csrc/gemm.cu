@@ -14,13 +14,16 @@ namespace srf {
 template <bool AT, bool BT, bool RELU_A, bool RELU_B>
 __global__ void __launch_bounds__(256)
 gemm64_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* C, int ldc, int M, int N, int K,
-              const float* __restrict__ bias, const float* __restrict__ mask, int ldm, const float* R, int ldr, int accumulate) {
+              const float* __restrict__ bias, const float* __restrict__ mask, int ldm, const float* R, int ldr, int accumulate,
+              int k_per) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  const int kbeg = blockIdx.z * k_per;                       // split-K as in gemm128_kernel
+  if (gridDim.z > 1) { K = min(K, kbeg + k_per); C += (size_t)blockIdx.z * M * ldc; }
+  for (int k0 = kbeg; k0 < K; k0 += 16) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int idx = threadIdx.x + e * 256;
@@ -231,8 +234,24 @@ static void dispatch(const GemmArgs& g, cudaStream_t st) {
     }
   } else {
     dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
-    gemm64_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.M, g.N, g.K, g.bias, g.mask, g.ldm,
-                                                        g.R, g.ldr, g.accumulate);
+    const int tiles = grid.x * grid.y;
+    int splits = 1;
+    if (g.splitk_ws && !g.bias && !g.mask && !g.R && tiles < 96 && g.K >= 1024) {
+      splits = (2 * 148 + tiles - 1) / tiles;
+      if (splits > 64) splits = 64;
+      while (splits > 1 && (size_t)splits * g.M * g.N > g.splitk_ws_floats) --splits;
+    }
+    if (splits > 1) {
+      int k_per = ((g.K + splits - 1) / splits + 15) / 16 * 16;
+      splits = (g.K + k_per - 1) / k_per;
+      grid.z = splits;
+      gemm64_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.splitk_ws, g.N, g.M, g.N, g.K, nullptr, nullptr, 0,
+                                                          nullptr, 0, 0, k_per);
+      splitk_reduce_kernel<<<(g.M * g.N + 255) / 256, 256, 0, st>>>(g.splitk_ws, splits, g.C, g.ldc, g.M, g.N, g.accumulate);
+    } else {
+      gemm64_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.M, g.N, g.K, g.bias, g.mask, g.ldm,
+                                                          g.R, g.ldr, g.accumulate, g.K);
+    }
   }
 }
 
