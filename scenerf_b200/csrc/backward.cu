@@ -196,6 +196,7 @@ struct GemmOpt {
   const float* R = nullptr; int ldr = 0;
   int accumulate = 0;
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
+  const int* skip = nullptr;
 };
 template <bool AT, bool BT, bool RA, bool RB>
 static void gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const GemmOpt& o,
@@ -204,7 +205,7 @@ static void gemm(const float* A, int lda, const float* B, int ldb, float* C, int
   g.A = A; g.lda = lda; g.at = AT; g.relu_a = RA; g.B = B; g.ldb = ldb; g.bt = BT; g.relu_b = RB;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   g.bias = o.bias; g.mask = o.mask; g.ldm = o.ldm; g.R = o.R; g.ldr = o.ldr; g.accumulate = o.accumulate;
-  g.splitk_ws = o.splitk_ws; g.splitk_ws_floats = o.splitk_ws_floats;
+  g.splitk_ws = o.splitk_ws; g.splitk_ws_floats = o.splitk_ws_floats; g.skip_if_zero = o.skip;
   launch_gemm(g, st);
 }
 
@@ -286,7 +287,7 @@ static inline int xin_ld_b(int d_latent) { return ((d_latent + kDX + 31) / 32) *
 
 size_t mlp_backward_workspace_bytes(int d_latent, int n_points) {
   const size_t m = (size_t)(n_points < kChunkB ? n_points : kChunkB);
-  return m * ((size_t)2 * xin_ld_b(d_latent) + 10 * kHidden) * sizeof(float) + kSplitKFloats * sizeof(float) + 256;
+  return m * ((size_t)2 * xin_ld_b(d_latent) + 10 * kHidden) * sizeof(float) + kSplitKFloats * sizeof(float) + 512;
 }
 
 // grads: same layout as the weights (accumulated into); pyramid grads CHW (accumulated into).  Returns launches or -1.
@@ -305,7 +306,8 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
   float* dH = q; q += cap * H;
   float* dN = q; q += cap * H;
   float* dP = q; q += cap * H;
-  float* SK = q;
+  float* SK = q; q += kSplitKFloats;
+  int* scale_any = reinterpret_cast<int*>(q);
   auto G = [](const float* c) { return const_cast<float*>(c); };
   PyrGrad gp;
   for (int s = 0; s < kScales; ++s) gp.chw[s] = grad_pyr_chw[s];
@@ -314,13 +316,17 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
     const int m = (n - p0) < kChunkB ? (n - p0) : kChunkB;
     const float* g_out = g_raw + (size_t)p0 * w.d_out;
     // ---- forward recompute, keeping pre-activations (resnetfc.py:133-164) ----
-    launch_build_xin(p, pts, viewdir, m, n_per, p0, X, ld, st);
+    launch_build_xin(p, pts, viewdir, m, n_per, p0, X, ld, nullptr, scale_any, st);
     GemmOpt o;
     o = GemmOpt(); o.bias = w.lin_in_b;
     gemm<false, true, false, false>(X + DL, ld, w.lin_in_w, kDX, PRE[0], H, m, H, kDX, o, st);                 // h0 = lin_in(x)
     for (int b = 0; b < 3; ++b) {
-      o = GemmOpt(); o.bias = w.lin_z_b[b]; o.R = (b == 0) ? PRE[0] : H3; o.ldr = H;
-      gemm<false, true, false, false>(X, ld, w.lin_z_w[b], DL, PRE[b], H, m, H, DL, o, st);                    // pre = h + lin_z(z)
+      for (int s = 0; s < kScales; ++s) {                                                                      // pre = h + lin_z(z), one K-segment per scale
+        o = GemmOpt();
+        if (s == 0) { o.bias = w.lin_z_b[b]; o.R = (b == 0) ? PRE[0] : H3; o.ldr = H; }
+        else { o.accumulate = 1; o.skip = scale_any + s; }
+        gemm<false, true, false, false>(X + p.ch_off[s], ld, w.lin_z_w[b] + p.ch_off[s], DL, PRE[b], H, m, H, p.C[s], o, st);
+      }
       o = GemmOpt(); o.bias = w.fc0_b[b];
       gemm<false, true, true, false>(PRE[b], H, w.fc0_w[b], H, NET[b], H, m, H, H, o, st);                     // net = fc_0(relu(pre))
       o = GemmOpt(); o.bias = w.fc1_b[b]; o.R = PRE[b]; o.ldr = H;
@@ -344,13 +350,15 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
       colsum(dN, H, m, H, G(gw.fc0_b[b]), SK, st);
       o = GemmOpt(); o.mask = PRE[b]; o.ldm = H; o.R = dH; o.ldr = H;
       gemm<false, false, false, false>(dN, H, w.fc0_w[b], H, dP, H, m, H, H, o, st);                           // dpre = dh + (dnet W_fc0) * (pre>0)
-      o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
-      gemm<true, false, false, false>(dP, H, X, ld, G(gw.lin_z_w[b]), DL, H, DL, m, o, st);                    // gW_linz += dpre^T z
+      for (int s = 0; s < kScales; ++s) {
+        o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats; o.skip = s ? scale_any + s : nullptr;
+        gemm<true, false, false, false>(dP, H, X + p.ch_off[s], ld, G(gw.lin_z_w[b]) + p.ch_off[s], DL, H, p.C[s], m, o, st);   // gW_linz += dpre^T z
+        o = GemmOpt(); o.accumulate = (b == 2) ? 0 : 1; o.skip = s ? scale_any + s : nullptr;
+        gemm<false, false, false, false>(dP, H, w.lin_z_w[b] + p.ch_off[s], DL, dZ + p.ch_off[s], ld, m, p.C[s], H, o, st);      // dz (+)= dpre W_linz
+      }
       colsum(dP, H, m, H, G(gw.lin_z_b[b]), SK, st);
-      o = GemmOpt(); o.accumulate = (b == 2) ? 0 : 1;
-      gemm<false, false, false, false>(dP, H, w.lin_z_w[b], DL, dZ, ld, m, DL, H, o, st);                      // dz (+)= dpre W_linz
       float* tmp = dH; dH = dP; dP = tmp;                                                                      // dh <- dpre
-      launches += 8;
+      launches += 16;
     }
     o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
     gemm<true, false, false, false>(dH, H, X + DL, ld, G(gw.lin_in_w), kDX, H, kDX, m, o, st);                 // gW_in += dh^T x

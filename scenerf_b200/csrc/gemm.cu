@@ -15,7 +15,8 @@ template <bool AT, bool BT, bool RELU_A, bool RELU_B>
 __global__ void __launch_bounds__(256)
 gemm64_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* C, int ldc, int M, int N, int K,
               const float* __restrict__ bias, const float* __restrict__ mask, int ldm, const float* R, int ldr, int accumulate,
-              int k_per) {
+              int k_per, const int* __restrict__ skip) {
+  if (skip && *skip == 0) return;                            // the whole K-segment is known to be zero (see GemmArgs::skip_if_zero)
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -122,7 +123,8 @@ template <bool AT, bool BT, bool RELU_A, bool RELU_B>
 __global__ void __launch_bounds__(256, 2)
 gemm128_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* C, int ldc, int M, int N, int K,
                const float* __restrict__ bias, const float* __restrict__ mask, int ldm, const float* R, int ldr, int accumulate,
-               int k_per) {
+               int k_per, const int* __restrict__ skip) {
+  if (skip && *skip == 0) return;
   __shared__ __align__(16) float As[2][kBK][kPitch];
   __shared__ __align__(16) float Bs[2][kBK][kPitch];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -189,7 +191,9 @@ gemm128_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
 
 // C[m][n] = (accumulate ? C[m][n] : 0) + sum_z part[z][m][n]   (z ascending: deterministic)
 __global__ void __launch_bounds__(256)
-splitk_reduce_kernel(const float* __restrict__ part, int splits, float* __restrict__ C, int ldc, int M, int N, int accumulate) {
+splitk_reduce_kernel(const float* __restrict__ part, int splits, float* __restrict__ C, int ldc, int M, int N, int accumulate,
+                     const int* __restrict__ skip) {
+  if (skip && *skip == 0) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * N) return;
   const int m = i / N, n = i % N;
@@ -226,11 +230,11 @@ static void dispatch(const GemmArgs& g, cudaStream_t st) {
       splits = (g.K + k_per - 1) / k_per;
       grid.z = splits;
       gemm128_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.splitk_ws, g.N, g.M, g.N, g.K, nullptr, nullptr, 0,
-                                                           nullptr, 0, 0, k_per);
-      splitk_reduce_kernel<<<(g.M * g.N + 255) / 256, 256, 0, st>>>(g.splitk_ws, splits, g.C, g.ldc, g.M, g.N, g.accumulate);
+                                                           nullptr, 0, 0, k_per, g.skip_if_zero);
+      splitk_reduce_kernel<<<(g.M * g.N + 255) / 256, 256, 0, st>>>(g.splitk_ws, splits, g.C, g.ldc, g.M, g.N, g.accumulate, g.skip_if_zero);
     } else {
       gemm128_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.M, g.N, g.K, g.bias, g.mask, g.ldm,
-                                                           g.R, g.ldr, g.accumulate, g.K);
+                                                           g.R, g.ldr, g.accumulate, g.K, g.skip_if_zero);
     }
   } else {
     dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
@@ -246,11 +250,11 @@ static void dispatch(const GemmArgs& g, cudaStream_t st) {
       splits = (g.K + k_per - 1) / k_per;
       grid.z = splits;
       gemm64_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.splitk_ws, g.N, g.M, g.N, g.K, nullptr, nullptr, 0,
-                                                          nullptr, 0, 0, k_per);
-      splitk_reduce_kernel<<<(g.M * g.N + 255) / 256, 256, 0, st>>>(g.splitk_ws, splits, g.C, g.ldc, g.M, g.N, g.accumulate);
+                                                          nullptr, 0, 0, k_per, g.skip_if_zero);
+      splitk_reduce_kernel<<<(g.M * g.N + 255) / 256, 256, 0, st>>>(g.splitk_ws, splits, g.C, g.ldc, g.M, g.N, g.accumulate, g.skip_if_zero);
     } else {
       gemm64_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.M, g.N, g.K, g.bias, g.mask, g.ldm,
-                                                          g.R, g.ldr, g.accumulate, g.K);
+                                                          g.R, g.ldr, g.accumulate, g.K, g.skip_if_zero);
     }
   }
 }

@@ -42,13 +42,17 @@ struct GemmArgs {
   const float* B = nullptr; int ldb = 0; bool bt = false; bool relu_b = false;
   float* C = nullptr; int ldc = 0; int M = 0, N = 0, K = 0;
   const float* bias = nullptr; const float* mask = nullptr; int ldm = 0; const float* R = nullptr; int ldr = 0; int accumulate = 0;
+  const int* skip_if_zero = nullptr;   // device flag: when *flag == 0 the launch does nothing (an all-zero K-segment of the latent)
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;   // optional scratch: enables deterministic split-K for long-K, few-tile shapes
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t st);    // 0, or -1 for an operand-layout combination that is not instantiated
 
 // one warp per point: X[i] = [ gathered latent (d_latent) | positional encoding (39) | viewdir (3) | 0-pad ], row stride ld
+//   scale_any (5 ints, or NULL): set to 1 for every scale at which some point of the chunk has an in-range bilinear tap.
+//   Scales whose flag stays 0 contribute exact zeros to x_in (quirk Q2: out-of-range normalised coordinates), so the
+//   lin_z GEMMs skip their K-segment -- bit-identical results.
 void launch_build_xin(const DevParams& p, const float* pts, const float* viewdir, int m, int n_per, int point0, float* X, int ld,
-                      cudaStream_t st);
+                      int32_t* dbg_sphere, int* scale_any, cudaStream_t st);
 
 // backward.cu : float32 backward of the path (reference: torch.autograd through scenerf.py:392-748)
 size_t mlp_backward_workspace_bytes(int d_latent, int n_points);

@@ -16,10 +16,11 @@ static inline int xin_ld(int d_latent) { return ((d_latent + kDX + 31) / 32) * 3
 // one warp per point: [ z (d_latent) | pe (39) | viewdir (3) | 0-pad ]
 __global__ void __launch_bounds__(256)
 build_xin_kernel(const __grid_constant__ DevParams p, const float* __restrict__ pts, const float* __restrict__ viewdir,
-                 int n, int n_per, int point0, float* __restrict__ X, int ld, int32_t* __restrict__ dbg_sphere) {
+                 int n, int n_per, int point0, float* __restrict__ X, int ld, int32_t* __restrict__ dbg_sphere,
+                 int* __restrict__ scale_any) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= n) return;
+  if (i >= n) return;                       // whole warp
   const int gi = point0 + i;
   const float x = pts[(size_t)gi * 3 + 0], y = pts[(size_t)gi * 3 + 1], z = pts[(size_t)gi * 3 + 2];
   int sx, sy;
@@ -29,6 +30,7 @@ build_xin_kernel(const __grid_constant__ DevParams p, const float* __restrict__ 
 #pragma unroll
   for (int s = 0; s < kScales; ++s) {
     const Taps t = scale_taps(p, s, sx, sy);
+    if (scale_any && t.any && lane == 0 && scale_any[s] == 0) atomicOr(&scale_any[s], 1);
     const float* f = reinterpret_cast<const float*>(p.feat[s]);
     float* dst = row + p.ch_off[s];
     for (int c = lane; c < p.C[s]; c += 32) {
@@ -76,20 +78,22 @@ lin_out_kernel(const float* __restrict__ Hh, const float* __restrict__ W, const 
 }
 
 void launch_build_xin(const DevParams& p, const float* pts, const float* viewdir, int m, int n_per, int point0, float* X, int ld,
-                      cudaStream_t st) {
-  build_xin_kernel<<<(m + 7) / 8, 256, 0, st>>>(p, pts, viewdir, m, n_per, point0, X, ld, nullptr);
+                      int32_t* dbg_sphere, int* scale_any, cudaStream_t st) {
+  if (scale_any) cudaMemsetAsync(scale_any, 0, kScales * sizeof(int), st);
+  build_xin_kernel<<<(m + 7) / 8, 256, 0, st>>>(p, pts, viewdir, m, n_per, point0, X, ld, dbg_sphere, scale_any);
 }
 
 size_t simt_workspace_bytes(int d_latent, int n_points) {
   const size_t chunk = (size_t)(n_points < kChunk ? n_points : kChunk);
-  return chunk * ((size_t)xin_ld(d_latent) + 2 * kHidden) * sizeof(float) + 256;
+  return chunk * ((size_t)xin_ld(d_latent) + 2 * kHidden) * sizeof(float) + 512;
 }
 
 // C[M x N] = (accumulate ? C : 0) + ( relu?(A)[M x K] * W[N x K]^T + bias )   (gemm.cu)
 template <bool kRelu>
 static void gemm(const float* A, int lda, const float* W, int ldw, const float* b, float* C, int M, int N, int K,
-                 int accumulate, cudaStream_t st) {
+                 int accumulate, cudaStream_t st, const int* skip = nullptr) {
   GemmArgs g;
+  g.skip_if_zero = skip;
   g.A = A; g.lda = lda; g.relu_a = kRelu; g.B = W; g.ldb = ldw; g.bt = true; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K;
   g.bias = b; g.accumulate = accumulate;
   launch_gemm(g, st);
@@ -104,17 +108,24 @@ int run_point_mlp_simt(const DevParams& p, const srf_mlp_weights& w, const float
   const int chunk_cap = n < kChunk ? n : kChunk;
   float* Hh = X + (size_t)chunk_cap * ld;
   float* Nn = Hh + (size_t)chunk_cap * kHidden;
+  int* scale_any = reinterpret_cast<int*>(Nn + (size_t)chunk_cap * kHidden);
   int launches = 0;
   for (int p0 = 0; p0 < n; p0 += kChunk) {
     const int m = (n - p0) < kChunk ? (n - p0) : kChunk;
-    build_xin_kernel<<<(m + 7) / 8, 256, 0, st>>>(p, pts, viewdir, m, n_per, p0, X, ld, dbg_sphere);
+    launch_build_xin(p, pts, viewdir, m, n_per, p0, X, ld, dbg_sphere, scale_any, st);
     ++launches;
     // h = lin_in(x)                               (resnetfc.py:148)
     gemm<false>(X + p.d_latent, ld, w.lin_in_w, kDX, w.lin_in_b, Hh, m, kHidden, kDX, 0, st);
     ++launches;
     for (int b = 0; b < SRF_NUM_BLOCKS; ++b) {
       // h = h + lin_z[b](z)                       (resnetfc.py:152-158)
-      gemm<false>(X, ld, w.lin_z_w[b], p.d_latent, w.lin_z_b[b], Hh, m, kHidden, p.d_latent, 1, st);
+      // one K-segment per pyramid scale; a scale no point of the chunk reaches is all zeros and is skipped on the device
+      for (int s = 0; s < kScales; ++s) {
+        gemm<false>(X + p.ch_off[s], ld, w.lin_z_w[b] + p.ch_off[s], p.d_latent, s == 0 ? w.lin_z_b[b] : nullptr, Hh, m, kHidden,
+                    p.C[s], 1, st, s == 0 ? nullptr : scale_any + s);
+        ++launches;
+      }
+      --launches;
       // net = fc_0(relu(h)); h = h + fc_1(relu(net))   (resnetfc.py:54-63)
       gemm<true>(Hh, kHidden, w.fc0_w[b], kHidden, w.fc0_b[b], Nn, m, kHidden, kHidden, 0, st);
       gemm<true>(Nn, kHidden, w.fc1_w[b], kHidden, w.fc1_b[b], Hh, m, kHidden, kHidden, 1, st);
