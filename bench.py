@@ -390,13 +390,81 @@ def run_train(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def run_lattice(args, rank, world, local):
+    """--workload E: density-only query of the 256^3 lattice (scenerf.py:505-547 `predict`), z-slab per GPU
+    + all-gather of the densities.  One step = the whole lattice (16.78 M points, 181.4 TFLOP)."""
+    import time
+    import torch
+    import torch.distributed as dist
+    from scenerf_b200 import synth, lattice
+    from scenerf_b200.renderer import B200Renderer
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = synth.config_A(name="lattice")
+    pm, pg = synth.make_model_params(cfg)
+    to = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    r = B200Renderer(hp_from_cfg(cfg), to(pm), to(pg), device=dev, precision=args.precision)
+    x_rgb = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_pyramid(5, cfg.sphere_W, cfg.sphere_H).items()}
+    K = torch.from_numpy(cfg.K).to(dev)
+    run = lambda: lattice.density_lattice(r, x_rgb, K, rank=rank, world=world)
+    for _ in range(args.warmup):
+        d = run()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        d = run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    n_pts = 256 ** 3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained") or 1400.0)
+    res = {"metric": "lattice points/sec (density query of the 256^3 lattice)", "value": n_pts / (ms * 1e-3), "unit": "points/s",
+           "ms_per_step": ms, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "dtype": args.precision, "data": "synthetic",
+           "scaling": "strong", "higher_is_better": True, "gpu_launches": int(r.last_lattice_launches),
+           "density_mean": float(d.mean()), "density_in_image_frac": float((d > 0).float().mean()),
+           "roofline": {"bound": "tensor", "achieved": n_pts * FLOP_MAIN / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": n_pts * FLOP_MAIN / (ms * 1e-3) / 1e12 / peak, "note": "whole step incl. point generation and z-slab all-gather"}}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle.scenerf_oracle import OracleRenderer
+        orc = OracleRenderer(cfg, pm, pg)
+        pyr = synth.make_pyramid(5, cfg.sphere_W, cfg.sphere_H)
+        xa = lattice.axis(*lattice.DEFAULT_X, "cpu").numpy(); ya = lattice.axis(*lattice.DEFAULT_Y, "cpu").numpy()
+        za = lattice.axis(*lattice.DEFAULT_Z, "cpu").numpy()
+        ncol = 32
+        pts = np.zeros((ncol, 256, 3), np.float32)
+        pts[:, :, 0] = xa[100:100 + ncol, None]; pts[:, :, 1] = ya[128]; pts[:, :, 2] = za[None, :]
+        t0 = time.perf_counter()
+        orc.predict(orc.pm, pts, pyr, cfg.K, np.tile(np.float32([[0, 0, 1]]), (ncol, 1)))
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": ncol * 256 / dt, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": "%d columns x 256 points with the numpy oracle (BLAS threads), %.1f s" % (ncol, dt)}
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="B", choices=["A", "B", "C", "sweep", "train"])
+    ap.add_argument("--workload", default="B", choices=["A", "B", "C", "E", "sweep", "train"])
     ap.add_argument("--sweep-poses", type=int, default=63)
     ap.add_argument("--sweep-scale", type=int, default=2)
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
@@ -414,6 +482,9 @@ def main():
         return
     if args.workload == "train":
         run_train(args, rank, world, local_rank)
+        return
+    if args.workload == "E":
+        run_lattice(args, rank, world, local_rank)
         return
     if args.impl == "reference":
         run_reference(args, rank, world)
