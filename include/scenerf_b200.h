@@ -218,6 +218,18 @@ int srf_tsdf_merge(float* tsdf_a, float* weight_a, float* color_a, const float* 
 int srf_upsample_render(const float* depth_xm, const float* color_xm, int gw, int gh, int out_h, int out_w,
                         float* depth_out, float* color_out, int color_mode, void* stream);
 
+/* --- next row (producer side): DecoderSphere.get_sphere_feature, scenerf/models/unet2d_sphere.py:138-166 ------------------
+ * x_chw_dev (C,h,w) float32 image-plane feature map of ONE image; pix_dev (n,2) float32 image pixels and
+ * pix_sphere_dev (n,2) int64 sphere pixels as SphericalMapping.from_pixels returns them (spherical_mapping.py:80-93);
+ * out_dev: (C,out_H,out_W) like the reference, or (out_H,out_W,C) when out_hwc != 0, with
+ * out_W = round(out_img_W/scale), out_H = round(out_img_H/scale) (Python round, half to even: query them with
+ * srf_sphere_feature_dims).  Sphere cells hit by several pixels keep the LAST pixel in index order (what the reference's
+ * index_put_ does on one CPU thread; on CUDA torch leaves it undefined).  workspace: out_W*out_H ints. */
+void srf_sphere_feature_dims(int out_img_W, int out_img_H, int scale, int* out_W, int* out_H);
+int srf_sphere_feature(const float* x_chw_dev, int C, int h, int w, const float* pix_dev, const long long* pix_sphere_dev,
+                       int n_pixels, int scale, int out_img_W, int out_img_H, float* out_dev, int out_hwc,
+                       void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Diagnostic (not part of the reference-facing surface): run the tensor-core point MLP of srf_predict but stop each
  * 128-point tile after layer `layer` of the tile program (mlp_tc.cu: 1 lin_in+lin_z0, 2 fc0_0, 4 fc1_0+lin_z1,
  * 5 fc0_1, 7 fc1_1+lin_z2, 8 fc0_2, 9 fc1_2, 10 lin_out) and write the raw fp32 accumulator rows to

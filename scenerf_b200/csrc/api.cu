@@ -522,6 +522,34 @@ int srf_upsample_render(const float* depth_xm, const float* color_xm, int gw, in
   return check_cuda("srf_upsample_render");
 }
 
+static int py_round_div(int a, int b) {            // Python round(a / b): half to even
+  const double q = (double)a / (double)b;
+  return (int)nearbyint(q);
+}
+
+void srf_sphere_feature_dims(int out_img_W, int out_img_H, int scale, int* out_W, int* out_H) {
+  if (out_W) *out_W = scale > 0 ? py_round_div(out_img_W, scale) : 0;
+  if (out_H) *out_H = scale > 0 ? py_round_div(out_img_H, scale) : 0;
+}
+
+int srf_sphere_feature(const float* x_chw_dev, int C, int h, int w, const float* pix_dev, const long long* pix_sphere_dev,
+                       int n_pixels, int scale, int out_img_W, int out_img_H, float* out_dev, int out_hwc,
+                       void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!x_chw_dev || !pix_dev || !pix_sphere_dev || !out_dev || !workspace_dev)
+    return fail(SRF_E_INVALID, "srf_sphere_feature: NULL argument");
+  if (C < 1 || h < 1 || w < 1 || n_pixels < 0 || scale < 1 || out_img_W < 1 || out_img_H < 1)
+    return fail(SRF_E_INVALID, "srf_sphere_feature: bad shape C=%d h=%d w=%d n=%d scale=%d", C, h, w, n_pixels, scale);
+  int oW, oH;
+  srf_sphere_feature_dims(out_img_W, out_img_H, scale, &oW, &oH);
+  if (oW < 1 || oH < 1) return fail(SRF_E_INVALID, "srf_sphere_feature: empty sphere grid at scale %d", scale);
+  if (workspace_bytes < (size_t)oW * oH * sizeof(int))
+    return fail(SRF_E_WORKSPACE, "srf_sphere_feature: workspace has %zu bytes, need %zu", workspace_bytes, (size_t)oW * oH * sizeof(int));
+  srf::launch_sphere_feature(x_chw_dev, C, h, w, pix_dev, pix_sphere_dev, n_pixels, scale, oW, oH,
+                             reinterpret_cast<int*>(workspace_dev), out_dev, out_hwc, (cudaStream_t)stream);
+  g_launches = 3;
+  return check_cuda("srf_sphere_feature");
+}
+
 int srf_debug_tc_layer(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w,
                        const float* cam_pts_dev, const float* viewdir_dev, int n_cols, int n_per, int layer,
                        float* acc_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {

@@ -36,6 +36,10 @@ int run_point_mlp_simt(const DevParams& p, const srf_mlp_weights& w, const float
                        int n_per, float* raw_out, int32_t* dbg_sphere, void* workspace, size_t ws_bytes,
                        cudaStream_t st);
 
+// sphere_feature.cu : image-plane feature map -> sphere grid (unet2d_sphere.py:138-166)
+void launch_sphere_feature(const float* x, int C, int h, int w, const float* pix, const long long* pix_sphere, int n, int scale,
+                           int oW, int oH, int* winner, float* out, int out_hwc, cudaStream_t st);
+
 // gemm.cu : float32 SIMT GEMM (see the file header for operand layouts and the epilogue)
 struct GemmArgs {
   const float* A = nullptr; int lda = 0; bool at = false; bool relu_a = false;

@@ -392,6 +392,34 @@ def grad_bf():
     return run_grad_case(cfg, synth.random_pixels(24, 40, cfg.img_W, cfg.img_H), pyr_seed=42)
 
 
+@case
+def sphere_feature():
+    """DecoderSphere.get_sphere_feature (unet2d_sphere.py:138-166): image-plane feature maps resampled onto the sphere grid
+    through the pixel -> sphere-pixel table of SphericalMapping.from_pixels.  Duplicate sphere cells are resolved by
+    index_put_ on ONE CPU thread, i.e. the last image pixel in row-major order wins."""
+    _install_shims()
+    from scenerf.models.unet2d_sphere import DecoderSphere
+    from scenerf.models.spherical_mapping import SphericalMapping
+    torch.set_num_threads(1)
+    W, H, oW, oH = 122, 37, 150, 45
+    K = synth.KITTI_K.copy()
+    K[:2] /= 10.0
+    cfg = synth.config_A(name="sf", sphere_W=oW, sphere_H=oH)
+    v0, v1, h0, h1 = cfg.angles()
+    sm = SphericalMapping(v_angle_max=v1, v_angle_min=v0, h_angle_max=h1, h_angle_min=h0, img_W=W, img_H=H, out_img_W=oW, out_img_H=oH)
+    pix, pix_sphere, _ = sm.from_pixels(inv_K=torch.inverse(torch.from_numpy(K)))
+    dec = DecoderSphere.__new__(DecoderSphere)
+    torch.nn.Module.__init__(dec)
+    dec.out_img_W, dec.out_img_H = oW, oH
+    out = dict(pix=pix.numpy(), pix_sphere=pix_sphere.numpy(), K=K, dims=np.array([W, H, oW, oH]))
+    for scale, C in ((1, 6), (2, 8), (4, 5)):
+        h, w = -(-H // scale), -(-W // scale)
+        x = torch.from_numpy(synth.hash_normalish(300 + scale, C * h * w).reshape(1, C, h, w).astype(np.float32))
+        out["x_%d" % scale] = x.numpy()[0]
+        out["feat_%d" % scale] = dec.get_sphere_feature(x, pix, pix_sphere, scale).numpy()[0]
+    return out
+
+
 def sweep_setup():
     """Small-image stand-in of generate_novel_depths.py: 244x74 image (KITTI intrinsics / 5), stride-4 grid (61x19 rays),
     the 6 poses of sample_rel_poses(step=1.0, angle=10, max_distance=1.1)."""
