@@ -100,6 +100,9 @@ typedef struct srf_config {
                                        fp16 instead of fp32 (GEMM accumulation stays fp32 in TMEM).  Halves the
                                        L2 traffic of the epilogues; h is rounded to fp16 as the next GEMM's operand
                                        anyway, measured effect on depth/colour error < 15 % of the fp16-mode error */
+#define SRF_FLAG_SAVE_ACTIVATIONS 4 /* float32 path, training: srf_render_rays keeps the ResnetFC pre-activations of both MLP
+                                       passes in its workspace (24.4 KB per sample point) so that srf_render_rays_backward
+                                       does not recompute the forward.  Outputs are bit-identical with and without it. */
 #define SRF_FLAG_SKIP_ZERO_CHUNKS 1 /* tensor-core path: skip K-chunks of lin_z whose gathered features are all
                                        zero for the whole 128-point tile (bit-identical result) */
 

@@ -56,6 +56,8 @@ class RenderRaysFunction(torch.autograd.Function):
         gauss = dict(zip(PARAM_KEYS, pg))
         w_main, w_gauss = _weights_struct(main, 4), _weights_struct(gauss, 2)
         cfg = r._config(cam_K, T)
+        if r.save_activations:
+            cfg.flags |= _lib.FLAG_SAVE_ACTIVATIONS       # the backward reads the pre-activations instead of recomputing them
         pyr = r._pack_pyramid(dict(zip(SCALE_KEYS, maps)))
         if pyr.format != _lib.PYR_FP32:
             raise RuntimeError("training needs a renderer built with precision='fp32'")
@@ -124,13 +126,16 @@ class TrainableRenderer:
     """`render_rays_batch` with the reference's signature whose outputs carry gradients to `mlp`, `mlp_gaussian`
     (any nn.Module / dict with the ResnetFC parameter names) and to the five maps of `x_rgb`."""
 
-    def __init__(self, hp: dict, mlp, mlp_gaussian, device="cuda:0", rng: str = "torch"):
+    def __init__(self, hp: dict, mlp, mlp_gaussian, device="cuda:0", rng: str = "torch", save_activations: bool = True):
         state = lambda m: dict(m.named_parameters()) if hasattr(m, "named_parameters") else dict(m)
         self.mlp, self.mlp_gaussian = mlp, mlp_gaussian
         self._state = state
         self.renderer = B200Renderer(hp, {k: v.detach() for k, v in state(mlp).items()},
                                      {k: v.detach() for k, v in state(mlp_gaussian).items()}, device=device, precision="fp32",
                                      rng=rng)
+        # True: keep the ResnetFC pre-activations of the forward (24.4 KB per sample point) for the backward;
+        # False: recompute them chunk by chunk in the backward (less memory, ~25 % more arithmetic)
+        self.renderer.save_activations = bool(save_activations)
 
     def render_rays_batch(self, cam_K, T_source2infer, x_rgb, depth_window=100, T_cam2velo=None, sampled_pixels=None,
                           ray_batch_size=128, *, noise=None):

@@ -151,11 +151,12 @@ void prof_record(int which, cudaStream_t st) {
 
 int run_mlp(const srf::DevParams& p, int precision, int flags, const srf_mlp_weights& w, const float* pts,
             const float* viewdir, int n, int n_per, float* raw, int32_t* dbg, void* ws, size_t ws_bytes,
-            cudaStream_t st) {
+            cudaStream_t st, void* saved = nullptr) {
   int l;
   const int pass = (w.d_out == 4) ? 1 : 0;
   prof_record(2 * pass, st);
-  if (precision == SRF_PREC_FP32) l = srf::run_point_mlp_simt(p, w, pts, viewdir, n, n_per, raw, dbg, ws, ws_bytes, st);
+  if (precision == SRF_PREC_FP32 && saved) l = srf::run_point_mlp_forward_save(p, w, pts, viewdir, n, n_per, raw, dbg, saved, st);
+  else if (precision == SRF_PREC_FP32) l = srf::run_point_mlp_simt(p, w, pts, viewdir, n, n_per, raw, dbg, ws, ws_bytes, st);
   else l = srf::run_point_mlp_tc(p, w, pts, viewdir, n, n_per, raw, dbg, flags, ws, ws_bytes, st);
   if (l < 0) return fail(SRF_E_WORKSPACE, "point-MLP workspace too small (%zu bytes)", ws_bytes);
   prof_record(2 * pass + 1, st);
@@ -173,6 +174,7 @@ struct RayWorkspace {
   float *unit, *viewdir, *gauss_pts, *gauss_raw, *means, *stds, *t_sorted, *depth_volume, *pts, *raw;
   void* mlp_ws;
   size_t mlp_ws_bytes;
+  void *saved_main, *saved_gauss;     // SRF_FLAG_SAVE_ACTIVATIONS (float32 training forward), else NULL
 };
 
 size_t carve(const srf_config* cfg, int R, int d_latent, unsigned char* base, RayWorkspace* out) {
@@ -193,6 +195,11 @@ size_t carve(const srf_config* cfg, int R, int d_latent, unsigned char* base, Ra
   const size_t m2 = mlp_workspace_bytes(cfg->precision, d_latent, (int)((size_t)R * G));
   w.mlp_ws_bytes = m1 > m2 ? m1 : m2;
   w.mlp_ws = a.take<unsigned char>(w.mlp_ws_bytes);
+  w.saved_main = w.saved_gauss = nullptr;
+  if ((cfg->flags & SRF_FLAG_SAVE_ACTIVATIONS) && cfg->precision == SRF_PREC_FP32) {
+    w.saved_main = a.take<unsigned char>(srf::mlp_saved_bytes(d_latent, (int)((size_t)R * S)));
+    w.saved_gauss = a.take<unsigned char>(srf::mlp_saved_bytes(d_latent, (int)((size_t)R * G)));
+  }
   if (out) *out = w;
   return a.off;
 }
@@ -296,7 +303,7 @@ int srf_render_rays(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp
   ++g_launches;
   if (int rc = check_cuda("ray_setup")) return rc;
   if (int rc = run_mlp(p, cfg->precision, cfg->flags, *w_gauss, ws.gauss_pts, ws.viewdir, R * G, G, ws.gauss_raw,
-                       out->dbg_sphere_gauss, ws.mlp_ws, ws.mlp_ws_bytes, st))
+                       out->dbg_sphere_gauss, ws.mlp_ws, ws.mlp_ws_bytes, st, ws.saved_gauss))
     return rc;
   float* means = out->gaussian_means ? out->gaussian_means : ws.means;
   float* stds = out->gaussian_stds ? out->gaussian_stds : ws.stds;
@@ -305,7 +312,7 @@ int srf_render_rays(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp
   ++g_launches;
   if (int rc = check_cuda("sample_sort")) return rc;
   if (int rc = run_mlp(p, cfg->precision, cfg->flags, *w_main, ws.pts, ws.viewdir, R * S, S, ws.raw,
-                       out->dbg_sphere_main, ws.mlp_ws, ws.mlp_ws_bytes, st))
+                       out->dbg_sphere_main, ws.mlp_ws, ws.mlp_ws_bytes, st, ws.saved_main))
     return rc;
   srf::launch_composite_som(p, R, ws.raw, ws.t_sorted, dv, means, stds, *out, st);
   ++g_launches;
@@ -466,13 +473,13 @@ int srf_render_rays_backward(const srf_config* cfg, const srf_pyramid* pyr, cons
                            graw_gauss, st);
   ++g_launches;
   if (int rc = check_cuda("ray_backward")) return rc;
-  int l = srf::run_point_mlp_backward_simt(p, *w_main, *grad_main, grad_pyr_chw, fw.pts, fw.viewdir, R * S, S, graw_main, mlp_ws,
-                                           mlp_ws_bytes, st);
+  int l = srf::run_point_mlp_backward_simt(p, *w_main, *grad_main, grad_pyr_chw, fw.pts, fw.viewdir, R * S, S, graw_main, fw.saved_main,
+                                           mlp_ws, mlp_ws_bytes, st);
   if (l < 0) return fail(SRF_E_WORKSPACE, "srf_render_rays_backward: MLP backward workspace too small");
   g_launches += l;
   if (int rc = check_cuda("main MLP backward")) return rc;
   l = srf::run_point_mlp_backward_simt(p, *w_gauss, *grad_gauss, grad_pyr_chw, fw.gauss_pts, fw.viewdir, R * G, G, graw_gauss,
-                                       mlp_ws, mlp_ws_bytes, st);
+                                       fw.saved_gauss, mlp_ws, mlp_ws_bytes, st);
   if (l < 0) return fail(SRF_E_WORKSPACE, "srf_render_rays_backward: MLP backward workspace too small");
   g_launches += l;
   return check_cuda("gaussian MLP backward");

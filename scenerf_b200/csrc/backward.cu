@@ -290,48 +290,110 @@ size_t mlp_backward_workspace_bytes(int d_latent, int n_points) {
   return m * ((size_t)2 * xin_ld_b(d_latent) + 10 * kHidden) * sizeof(float) + kSplitKFloats * sizeof(float) + 512;
 }
 
-// grads: same layout as the weights (accumulated into); pyramid grads CHW (accumulated into).  Returns launches or -1.
+// Activations of the float32 forward that the backward needs, for ALL points of a pass (SRF_FLAG_SAVE_ACTIVATIONS): the
+// training forward writes them once and the backward skips its recompute.  Layout: X (n,ld) | PRE[3] NET[3] H3 (n,512) |
+// per-chunk scale flags (8 ints per chunk).
+struct SavedActs { float* X; float* PRE[3]; float* NET[3]; float* H3; int* flags; };
+static inline size_t n_chunks_b(int n) { return ((size_t)n + kChunkB - 1) / kChunkB; }
+size_t mlp_saved_bytes(int d_latent, int n_points) {
+  return (size_t)n_points * ((size_t)xin_ld_b(d_latent) + 7 * kHidden) * sizeof(float) + n_chunks_b(n_points) * 8 * sizeof(int) + 256;
+}
+static SavedActs saved_view(void* base, int d_latent, int n) {
+  SavedActs a;
+  float* q = reinterpret_cast<float*>(base);
+  a.X = q; q += (size_t)n * xin_ld_b(d_latent);
+  for (int b = 0; b < 3; ++b) { a.PRE[b] = q; q += (size_t)n * kHidden; a.NET[b] = q; q += (size_t)n * kHidden; }
+  a.H3 = q; q += (size_t)n * kHidden;
+  a.flags = reinterpret_cast<int*>(q);
+  return a;
+}
+
+// resnetfc.py:133-164 for m points keeping the pre-activations: PRE[b] = h + lin_z_b(z), NET[b] = fc_0(relu(PRE[b])),
+// H3 = h after block 2.  Returns launches.
+static int forward_chunk(const DevParams& p, const srf_mlp_weights& w, const float* X, int ld, float* const* PRE, float* const* NET,
+                         float* H3, int m, const int* scale_any, cudaStream_t st) {
+  const int H = kHidden, DL = p.d_latent;
+  GemmOpt o;
+  o.bias = w.lin_in_b;
+  gemm<false, true, false, false>(X + DL, ld, w.lin_in_w, kDX, PRE[0], H, m, H, kDX, o, st);                   // h0 = lin_in(x)
+  int launches = 1;
+  for (int b = 0; b < 3; ++b) {
+    for (int s = 0; s < kScales; ++s) {                                                                        // pre = h + lin_z(z), one K-segment per scale
+      o = GemmOpt();
+      if (s == 0) { o.bias = w.lin_z_b[b]; o.R = (b == 0) ? PRE[0] : H3; o.ldr = H; }
+      else { o.accumulate = 1; o.skip = scale_any + s; }
+      gemm<false, true, false, false>(X + p.ch_off[s], ld, w.lin_z_w[b] + p.ch_off[s], DL, PRE[b], H, m, H, p.C[s], o, st);
+    }
+    o = GemmOpt(); o.bias = w.fc0_b[b];
+    gemm<false, true, true, false>(PRE[b], H, w.fc0_w[b], H, NET[b], H, m, H, H, o, st);                       // net = fc_0(relu(pre))
+    o = GemmOpt(); o.bias = w.fc1_b[b]; o.R = PRE[b]; o.ldr = H;
+    gemm<false, true, true, false>(NET[b], H, w.fc1_w[b], H, H3, H, m, H, H, o, st);                           // h = pre + fc_1(relu(net))
+    launches += kScales + 2;
+  }
+  return launches;
+}
+
+// Training forward of one pass: same arithmetic as run_point_mlp_simt (bit-identical raw outputs), activations kept.
+int run_point_mlp_forward_save(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n, int n_per,
+                               float* raw_out, int32_t* dbg_sphere, void* saved_base, cudaStream_t st) {
+  const int ld = xin_ld_b(p.d_latent), H = kHidden;
+  const SavedActs a = saved_view(saved_base, p.d_latent, n);
+  int launches = 0, chunk = 0;
+  for (int p0 = 0; p0 < n; p0 += kChunkB, ++chunk) {
+    const int m = (n - p0) < kChunkB ? (n - p0) : kChunkB;
+    float* X = a.X + (size_t)p0 * ld;
+    float* PRE[3]; float* NET[3];
+    for (int b = 0; b < 3; ++b) { PRE[b] = a.PRE[b] + (size_t)p0 * H; NET[b] = a.NET[b] + (size_t)p0 * H; }
+    float* H3 = a.H3 + (size_t)p0 * H;
+    int* flags = a.flags + chunk * 8;
+    launch_build_xin(p, pts, viewdir, m, n_per, p0, X, ld, dbg_sphere, flags, st);
+    launches += 1 + forward_chunk(p, w, X, ld, PRE, NET, H3, m, flags, st);
+    launch_lin_out(H3, w.lin_out_w, w.lin_out_b, raw_out + (size_t)p0 * w.d_out, m, w.d_out, st);
+    ++launches;
+  }
+  return launches;
+}
+
+// grads: same layout as the weights (accumulated into); pyramid grads CHW (accumulated into).  saved_base: activations of
+// run_point_mlp_forward_save for the same points, or NULL (the forward is then recomputed chunk by chunk).
+// Returns launches or -1.
 int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, const srf_mlp_weights& gw, float* const* grad_pyr_chw,
-                                const float* pts, const float* viewdir, int n, int n_per, const float* g_raw, void* workspace,
-                                size_t ws_bytes, cudaStream_t st) {
+                                const float* pts, const float* viewdir, int n, int n_per, const float* g_raw, const void* saved_base,
+                                void* workspace, size_t ws_bytes, cudaStream_t st) {
   if (ws_bytes < mlp_backward_workspace_bytes(p.d_latent, n)) return -1;
   const int ld = xin_ld_b(p.d_latent), H = kHidden, DL = p.d_latent;
   const size_t cap = (size_t)(n < kChunkB ? n : kChunkB);
-  float* X = reinterpret_cast<float*>(workspace);
-  float* dZ = X + cap * ld;
-  float* PRE[3]; float* NET[3];
+  float* Xc = reinterpret_cast<float*>(workspace);
+  float* dZ = Xc + cap * ld;
+  float* PREc[3]; float* NETc[3];
   float* q = dZ + cap * ld;
-  for (int b = 0; b < 3; ++b) { PRE[b] = q; q += cap * H; NET[b] = q; q += cap * H; }
-  float* H3 = q; q += cap * H;
+  for (int b = 0; b < 3; ++b) { PREc[b] = q; q += cap * H; NETc[b] = q; q += cap * H; }
+  float* H3c = q; q += cap * H;
   float* dH = q; q += cap * H;
   float* dN = q; q += cap * H;
   float* dP = q; q += cap * H;
   float* SK = q; q += kSplitKFloats;
-  int* scale_any = reinterpret_cast<int*>(q);
+  int* flags_c = reinterpret_cast<int*>(q);
+  SavedActs sv;
+  if (saved_base) sv = saved_view(const_cast<void*>(saved_base), p.d_latent, n);
   auto G = [](const float* c) { return const_cast<float*>(c); };
   PyrGrad gp;
   for (int s = 0; s < kScales; ++s) gp.chw[s] = grad_pyr_chw[s];
-  int launches = 0;
-  for (int p0 = 0; p0 < n; p0 += kChunkB) {
+  int launches = 0, chunk = 0;
+  for (int p0 = 0; p0 < n; p0 += kChunkB, ++chunk) {
     const int m = (n - p0) < kChunkB ? (n - p0) : kChunkB;
     const float* g_out = g_raw + (size_t)p0 * w.d_out;
-    // ---- forward recompute, keeping pre-activations (resnetfc.py:133-164) ----
-    launch_build_xin(p, pts, viewdir, m, n_per, p0, X, ld, nullptr, scale_any, st);
+    float* X = Xc; float* H3 = H3c; int* scale_any = flags_c;
+    float* PRE[3] = {PREc[0], PREc[1], PREc[2]};
+    float* NET[3] = {NETc[0], NETc[1], NETc[2]};
     GemmOpt o;
-    o = GemmOpt(); o.bias = w.lin_in_b;
-    gemm<false, true, false, false>(X + DL, ld, w.lin_in_w, kDX, PRE[0], H, m, H, kDX, o, st);                 // h0 = lin_in(x)
-    for (int b = 0; b < 3; ++b) {
-      for (int s = 0; s < kScales; ++s) {                                                                      // pre = h + lin_z(z), one K-segment per scale
-        o = GemmOpt();
-        if (s == 0) { o.bias = w.lin_z_b[b]; o.R = (b == 0) ? PRE[0] : H3; o.ldr = H; }
-        else { o.accumulate = 1; o.skip = scale_any + s; }
-        gemm<false, true, false, false>(X + p.ch_off[s], ld, w.lin_z_w[b] + p.ch_off[s], DL, PRE[b], H, m, H, p.C[s], o, st);
-      }
-      o = GemmOpt(); o.bias = w.fc0_b[b];
-      gemm<false, true, true, false>(PRE[b], H, w.fc0_w[b], H, NET[b], H, m, H, H, o, st);                     // net = fc_0(relu(pre))
-      o = GemmOpt(); o.bias = w.fc1_b[b]; o.R = PRE[b]; o.ldr = H;
-      gemm<false, true, true, false>(NET[b], H, w.fc1_w[b], H, H3, H, m, H, H, o, st);                         // h = pre + fc_1(relu(net))
-      launches += 3;
+    if (saved_base) {
+      X = sv.X + (size_t)p0 * ld; H3 = sv.H3 + (size_t)p0 * H; scale_any = sv.flags + chunk * 8;
+      for (int b = 0; b < 3; ++b) { PRE[b] = sv.PRE[b] + (size_t)p0 * H; NET[b] = sv.NET[b] + (size_t)p0 * H; }
+    } else {
+      // ---- forward recompute, keeping pre-activations (resnetfc.py:133-164) ----
+      launch_build_xin(p, pts, viewdir, m, n_per, p0, X, ld, nullptr, scale_any, st);
+      launches += 1 + forward_chunk(p, w, X, ld, PRE, NET, H3, m, scale_any, st);
     }
     // ---- backward ----
     o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;

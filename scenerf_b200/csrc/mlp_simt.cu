@@ -83,6 +83,10 @@ void launch_build_xin(const DevParams& p, const float* pts, const float* viewdir
   build_xin_kernel<<<(m + 7) / 8, 256, 0, st>>>(p, pts, viewdir, m, n_per, point0, X, ld, dbg_sphere, scale_any);
 }
 
+void launch_lin_out(const float* Hh, const float* W, const float* bias, float* out, int M, int d_out, cudaStream_t st) {
+  lin_out_kernel<<<(M + 7) / 8, 256, 0, st>>>(Hh, W, bias, out, M, d_out);
+}
+
 size_t simt_workspace_bytes(int d_latent, int n_points) {
   const size_t chunk = (size_t)(n_points < kChunk ? n_points : kChunk);
   return chunk * ((size_t)xin_ld(d_latent) + 2 * kHidden) * sizeof(float) + 512;

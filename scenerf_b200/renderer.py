@@ -103,6 +103,7 @@ class B200Renderer:
         self.seed = 0x5CE9E2F
         self.last_launches = 0
         self.last_backward_launches = 0
+        self.save_activations = False
 
     # ------------------------------------------------------------------------------------------------------------
     @classmethod

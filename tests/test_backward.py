@@ -113,7 +113,7 @@ def test_mlp_backward_oracle_against_finite_differences():
 
 # ------------------------------------------------------------------------------------------------ GPU
 
-def _run_cuda(name):
+def _run_cuda(name, save_activations=True):
     import torch
     from helpers import hp_from_cfg
     from scenerf_b200.autograd import TrainableRenderer, PARAM_KEYS
@@ -124,7 +124,7 @@ def _run_cuda(name):
     mk = lambda d: {k: torch.from_numpy(d[k]).to(dev).requires_grad_(True) for k in PARAM_KEYS}
     tm, tg = mk(pm), mk(pg)
     x_rgb = {k: torch.from_numpy(v).to(dev).requires_grad_(True) for k, v in synth.make_pyramid(seed, cfg.sphere_W, cfg.sphere_H).items()}
-    t = TrainableRenderer(hp_from_cfg(cfg), tm, tg, device=dev)
+    t = TrainableRenderer(hp_from_cfg(cfg), tm, tg, device=dev, save_activations=save_activations)
     out = t.render_rays_batch(torch.from_numpy(cfg.K), torch.from_numpy(cfg.T), x_rgb, sampled_pixels=torch.from_numpy(g["pixels"]),
                               ray_batch_size=g["pixels"].shape[0],
                               noise=(torch.from_numpy(g["noise_u"]), torch.from_numpy(g["noise_n"])))
@@ -171,6 +171,11 @@ def test_cuda_backward_matches_float64_oracle_and_is_reproducible():
     g2, _, _, _, _, tm2, tg2, x2, _ = _run_cuda(name)
     for k in tm:
         assert (tm[k].grad == tm2[k].grad).all() and (tg[k].grad == tg2[k].grad).all(), k
+    # recomputing the forward inside the backward (save_activations=False) is the same arithmetic: identical gradients
+    g3, _, _, out3, _, tm3, tg3, x3, _ = _run_cuda(name, save_activations=False)
+    assert all((out[k] == out3[k]).all() for k in out)
+    for k in tm:
+        assert (tm[k].grad == tm3[k].grad).all() and (tg[k].grad == tg3[k].grad).all(), k
 
 
 @pytest.mark.gpu
