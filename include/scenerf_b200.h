@@ -233,6 +233,13 @@ int srf_sphere_feature(const float* x_chw_dev, int C, int h, int w, const float*
                        int n_pixels, int scale, int out_img_W, int out_img_H, float* out_dev, int out_hwc,
                        void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Diagnostic: one GEMM of the training path, C[M x N] = epilogue(A[M x K] * B[N x K]^T) with float32 device operands.
+ * use_tf32 != 0 runs the tcgen05 kind::tf32 kernel (csrc/gemm_tf32.cu), 0 the float32 SIMT kernel (csrc/gemm.cu).
+ * bias (N) / mask (M x N, keeps values where mask > 0) / residual (M x N) may be NULL; splitk_ws enables split-K. */
+int srf_debug_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const float* bias,
+                   const float* mask, int ldm, const float* residual, int ldr, int accumulate, float* splitk_ws,
+                   size_t splitk_ws_floats, int use_tf32, void* stream);
+
 /* Diagnostic (not part of the reference-facing surface): run the tensor-core point MLP of srf_predict but stop each
  * 128-point tile after layer `layer` of the tile program (mlp_tc.cu: 1 lin_in+lin_z0, 2 fc0_0, 4 fc1_0+lin_z1,
  * 5 fc0_1, 7 fc1_1+lin_z2, 8 fc0_2, 9 fc1_2, 10 lin_out) and write the raw fp32 accumulator rows to

@@ -529,6 +529,22 @@ int srf_upsample_render(const float* depth_xm, const float* color_xm, int gw, in
   return check_cuda("srf_upsample_render");
 }
 
+int srf_debug_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const float* bias,
+                   const float* mask, int ldm, const float* residual, int ldr, int accumulate, float* splitk_ws,
+                   size_t splitk_ws_floats, int use_tf32, void* stream) {
+  if (!A || !B || !C || M < 1 || N < 1 || K < 1) return fail(SRF_E_INVALID, "srf_debug_gemm: bad argument");
+  srf::GemmArgs g;
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.bt = true; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  g.bias = bias; g.mask = mask; g.ldm = ldm; g.R = residual; g.ldr = ldr; g.accumulate = accumulate;
+  g.splitk_ws = splitk_ws; g.splitk_ws_floats = splitk_ws_floats;
+  const int rc = use_tf32 ? srf::launch_gemm_tf32(g, (cudaStream_t)stream) : srf::launch_gemm(g, (cudaStream_t)stream);
+  if (rc) return fail(SRF_E_INVALID, "srf_debug_gemm: shape not supported by the %s kernel", use_tf32 ? "tf32" : "simt");
+  g_launches = 1;
+  const int e = check_cuda("srf_debug_gemm");
+  if (e && use_tf32) return fail(SRF_E_CUDA, "srf_debug_gemm: %s (tf32 watchdog flag 0x%x)", srf_last_error(), srf::tf32_watchdog_flag());
+  return e;
+}
+
 static int py_round_div(int a, int b) {            // Python round(a / b): half to even
   const double q = (double)a / (double)b;
   return (int)nearbyint(q);

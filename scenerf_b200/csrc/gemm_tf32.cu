@@ -1,0 +1,259 @@
+// TF32 tensor-core GEMM for the training path:  C[M x N] = epilogue( A[M x K] * B[N x K]^T ),  A and B float32, both
+// K-contiguous ("NT"), accumulation in float32 in tensor memory.  tcgen05.mma kind::tf32 reads the float32 operands
+// straight from shared memory (top 19 bits), so there is no conversion pass: TMA (cp.async.bulk.tensor.2d, 128-byte
+// swizzle) stages 128 x 32 float tiles of A and B, one elected thread issues 4 MMAs (K = 8 each) per stage into a
+// 128 x 128 fp32 accumulator (128 TMEM columns), tcgen05.commit releases the stage, 4 epilogue warps read the
+// accumulator with tcgen05.ld and apply the same epilogue as gemm.cu (bias, ReLU mask, residual, accumulate).
+// One output tile per CTA, 3 stages (96 KB) so that two CTAs share an SM and one's epilogue overlaps the other's main
+// loop; split-K over gridDim.z with fixed-order reduction for the weight-gradient shapes.
+// Roofline: tensor pipe (tf32 = half the f16 rate) -- and L2->SM bandwidth: a 128x128 tile moves 32 KB per 1.05 MFLOP.
+#include <cuda.h>
+#include "kernels.cuh"
+
+namespace srf {
+namespace tf32 {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32, kStages = 3;
+constexpr uint32_t kTileBytes = kBM * kBK * 4;            // 16 KB
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 2000000000LL) { if (err) atomicExch(err, (int)(0x54000000u | (bar & 0xFFFFFF))); __trap(); }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (same encoding as mlp_tc.cu: make_desc_sw128)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: c_format F32 (1) at [4,6), a/b format TF32 (2) at [7,10) / [10,13), K-major, N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+__global__ void __launch_bounds__(kThreads)
+gemm_tf32_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* C, int ldc, int M, int N,
+                    int K, const float* __restrict__ bias, const float* __restrict__ mask, int ldm, const float* R, int ldr,
+                    int accumulate, int k_per, const int* __restrict__ skip, int* err) {
+  if (skip && *skip == 0) return;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t sA = base, sB = base + kStages * kTileBytes;
+  const uint32_t bars = sB + kStages * kTileBytes;                        // full[kStages], empty[kStages], acc
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const int kbeg = blockIdx.z * k_per;
+  const int kend = min(K, kbeg + k_per);
+  const int nk = (kend - kbeg + kBK - 1) / kBK;
+  if (gridDim.z > 1) C += (size_t)blockIdx.z * M * ldc;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (kStages + s), 1); }
+    mbar_init(bars + 8u * (2 * kStages), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % kStages;
+        mbar_wait(bars + 8u * (kStages + s), (((uint32_t)(i / kStages)) & 1u) ^ 1u, err);
+        mbar_arrive_expect_tx(bars + 8u * s, 2 * kTileBytes);
+        tma_load_2d(sA + s * kTileBytes, &tmA, kbeg + i * kBK, m0, bars + 8u * s);
+        tma_load_2d(sB + s * kTileBytes, &tmB, kbeg + i * kBK, n0, bars + 8u * s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % kStages;
+        mbar_wait(bars + 8u * s, ((uint32_t)(i / kStages)) & 1u, err);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int k4 = 0; k4 < kBK / 8; ++k4)
+          umma_tf32(tmem, make_desc_sw128(sA + s * kTileBytes + k4 * 32), make_desc_sw128(sB + s * kTileBytes + k4 * 32), kIdesc,
+                    (i > 0 || k4 > 0) ? 1u : 0u);
+        umma_commit(bars + 8u * (kStages + s));            // stage free once these MMAs have read it
+      }
+      umma_commit(bars + 8u * (2 * kStages));              // accumulator complete
+    }
+  } else {
+    const int q = warp & 3;                                 // TMEM lane quarter this warp may read
+    const int gm = m0 + q * 32 + lane;
+    if (nk > 0) mbar_wait(bars + 8u * (2 * kStages), 0, err);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int c = 0; c < kBN / 32; ++c) {
+      uint32_t v[32];
+      if (nk > 0) {
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (gm < M) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int gn = n0 + c * 32 + j4 * 4;
+          if (gn >= N) break;                              // N % 4 == 0
+          float4 o = make_float4(__uint_as_float(v[j4 * 4]), __uint_as_float(v[j4 * 4 + 1]), __uint_as_float(v[j4 * 4 + 2]),
+                                 __uint_as_float(v[j4 * 4 + 3]));
+          if (bias) { const float4 t = *reinterpret_cast<const float4*>(bias + gn); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+          if (mask) {
+            const float4 t = *reinterpret_cast<const float4*>(mask + (size_t)gm * ldm + gn);
+            o.x = t.x > 0.f ? o.x : 0.f; o.y = t.y > 0.f ? o.y : 0.f; o.z = t.z > 0.f ? o.z : 0.f; o.w = t.w > 0.f ? o.w : 0.f;
+          }
+          if (R) { const float4 t = *reinterpret_cast<const float4*>(R + (size_t)gm * ldr + gn); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+          float4* dst = reinterpret_cast<float4*>(C + (size_t)gm * ldc + gn);
+          if (accumulate) { const float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+          *dst = o;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, int splits, float* __restrict__ C, int ldc, int M, int N, int accumulate,
+                     const int* __restrict__ skip) {
+  if (skip && *skip == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += part[(size_t)z * M * N + i];
+  float* dst = C + (size_t)(i / N) * ldc + (i % N);
+  *dst = accumulate ? (*dst + v) : v;
+}
+
+}  // namespace tf32
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tf32_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// rows x K float32 matrix with row stride ld (elements): box = 128 rows x 32 floats, 128-byte swizzle
+static bool encode_f32(CUtensorMap* tm, const float* base, int rows, int K, int ld) {
+  EncodeTiledFn fn = tf32_encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)tf32::kBK, (cuuint32_t)tf32::kBM};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int* g_tf32_err = nullptr;       // mapped host flag written by the watchdog
+int tf32_watchdog_flag() { return g_tf32_err ? *reinterpret_cast<volatile int*>(g_tf32_err) : 0; }
+
+// Only the NT layout with un-transformed operands (at=false, bt=true, no relu_a / relu_b).  Returns 0, or -1 when the
+// shape cannot go through TMA (unaligned rows) -- the caller then falls back to launch_gemm.
+int launch_gemm_tf32(const GemmArgs& g, cudaStream_t st) {
+  if (g.at || !g.bt || g.relu_a || g.relu_b) return -1;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if ((g.lda % 4) || (g.ldb % 4) || (g.ldc % 4) || (g.N % 4) || !al16(g.A) || !al16(g.B) || !al16(g.C)) return -1;
+  if ((g.bias && !al16(g.bias)) || (g.mask && (!al16(g.mask) || g.ldm % 4)) || (g.R && (!al16(g.R) || g.ldr % 4))) return -1;
+  CUtensorMap tmA, tmB;
+  if (!encode_f32(&tmA, g.A, g.M, g.K, g.lda) || !encode_f32(&tmB, g.B, g.N, g.K, g.ldb)) return -1;
+  if (!g_tf32_err) {
+    int* h = nullptr;
+    if (cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped) == cudaSuccess) { *h = 0; cudaHostGetDevicePointer(&g_tf32_err, h, 0); }
+  }
+  static bool attr = false;
+  const size_t smem = 2 * tf32::kStages * tf32::kTileBytes + 1024 + 256;
+  if (!attr) { cudaFuncSetAttribute(tf32::gemm_tf32_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  dim3 grid((g.N + tf32::kBN - 1) / tf32::kBN, (g.M + tf32::kBM - 1) / tf32::kBM);
+  const int tiles = grid.x * grid.y;
+  int splits = 1;
+  if (g.splitk_ws && !g.bias && !g.mask && !g.R && tiles < 96 && g.K >= 1024) {
+    splits = (2 * 148 + tiles - 1) / tiles;
+    if (splits > 32) splits = 32;
+    while (splits > 1 && (size_t)splits * g.M * g.N > g.splitk_ws_floats) --splits;
+  }
+  if (splits > 1) {
+    const int k_per = ((g.K + splits - 1) / splits + tf32::kBK - 1) / tf32::kBK * tf32::kBK;
+    splits = (g.K + k_per - 1) / k_per;
+    grid.z = splits;
+    tf32::gemm_tf32_nt_kernel<<<grid, tf32::kThreads, smem, st>>>(tmA, tmB, g.splitk_ws, g.N, g.M, g.N, g.K, nullptr, nullptr, 0, nullptr, 0,
+                                                                  0, k_per, g.skip_if_zero, g_tf32_err);
+    tf32::splitk_reduce_kernel<<<(g.M * g.N + 255) / 256, 256, 0, st>>>(g.splitk_ws, splits, g.C, g.ldc, g.M, g.N, g.accumulate,
+                                                                        g.skip_if_zero);
+  } else {
+    tf32::gemm_tf32_nt_kernel<<<grid, tf32::kThreads, smem, st>>>(tmA, tmB, g.C, g.ldc, g.M, g.N, g.K, g.bias, g.mask, g.ldm, g.R, g.ldr,
+                                                                  g.accumulate, g.K, g.skip_if_zero, g_tf32_err);
+  }
+  return 0;
+}
+
+}  // namespace srf

@@ -51,6 +51,11 @@ struct GemmArgs {
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t st);    // 0, or -1 for an operand-layout combination that is not instantiated
 
+// gemm_tf32.cu : the same contract on tensor cores (tcgen05 kind::tf32, float32 operands read in place); NT layout only
+// (at=false, bt=true, no operand ReLU).  Returns 0, or -1 when the shape cannot be expressed as TMA tensor maps.
+int launch_gemm_tf32(const GemmArgs& g, cudaStream_t st);
+int tf32_watchdog_flag();
+
 // one warp per point: X[i] = [ gathered latent (d_latent) | positional encoding (39) | viewdir (3) | 0-pad ], row stride ld
 //   scale_any (5 ints, or NULL): set to 1 for every scale at which some point of the chunk has an in-range bilinear tap.
 //   Scales whose flag stays 0 contribute exact zeros to x_in (quirk Q2: out-of-range normalised coordinates), so the
