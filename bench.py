@@ -312,7 +312,7 @@ def run_train(args, rank, world, local):
     mk = lambda d: {k: torch.from_numpy(d[k]).to(dev).requires_grad_(True) for k in PARAM_KEYS}
     tm, tg = mk(pm), mk(pg)
     x_rgb = {k: torch.from_numpy(v).to(dev).requires_grad_(True) for k, v in synth.make_pyramid(5 + rank, cfg.sphere_W, cfg.sphere_H).items()}
-    t = TrainableRenderer(hp_from_cfg(cfg), tm, tg, device=dev, rng="philox")
+    t = TrainableRenderer(hp_from_cfg(cfg), tm, tg, device=dev, rng="philox", matmul=args.train_matmul)
     K, T = torch.from_numpy(cfg.K).to(dev), torch.from_numpy(cfg.T).to(dev)
     grid = synth.grid_pixels(cfg.img_W, cfg.img_H, stride=2)
     sel = np.random.default_rng(7 + rank).permutation(grid.shape[0])[:R]
@@ -361,7 +361,8 @@ def run_train(args, rank, world, local):
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # 148 SMs x 128 FMA lanes x 2 x max clock
     res = {"metric": "training rays/sec (render_rays_batch forward + backward, %d rays x %d samples per step)" % (R, cfg.S),
            "value": world * R / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "dtype": "f32", "data": "synthetic", "scaling": "weak", "higher_is_better": True,
+           "warmup": args.warmup, "dtype": "f32" if args.train_matmul == "fp32" else "tf32 operands, f32 storage and accumulate",
+           "data": "synthetic", "scaling": "weak", "higher_is_better": True,
            "forward_ms": fwd_ms, "backward_ms": bwd_ms, "loss": lv,
            "gpu_launches": int(t.renderer.last_launches + t.renderer.last_backward_launches),
            "roofline": {"bound": "fp32 FMA (SIMT)", "achieved": 3.0 * flop_fwd / (ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -465,6 +466,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="B", choices=["A", "B", "C", "E", "sweep", "train"])
+    ap.add_argument("--train-matmul", default="fp32", choices=["fp32", "tf32"], help="--workload train: GEMM engine")
     ap.add_argument("--sweep-poses", type=int, default=63)
     ap.add_argument("--sweep-scale", type=int, default=2)
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])

@@ -100,6 +100,11 @@ typedef struct srf_config {
                                        fp16 instead of fp32 (GEMM accumulation stays fp32 in TMEM).  Halves the
                                        L2 traffic of the epilogues; h is rounded to fp16 as the next GEMM's operand
                                        anyway, measured effect on depth/colour error < 15 % of the fp16-mode error */
+#define SRF_FLAG_TF32_MATMUL 8      /* float32 path, training (needs SRF_FLAG_SAVE_ACTIVATIONS in the forward): the GEMMs of the
+                                       forward and of srf_render_rays_backward run on tensor cores as tcgen05 kind::tf32
+                                       (float32 storage, 10-bit mantissa operands, float32 accumulate) -- the regime of the
+                                       reference's own torch 1.7.1 defaults on Ampere-class GPUs.  Not bit-compatible with
+                                       the strict float32 mode; tolerances in DESIGN.md 6.3. */
 #define SRF_FLAG_SAVE_ACTIVATIONS 4 /* float32 path, training: srf_render_rays keeps the ResnetFC pre-activations of both MLP
                                        passes in its workspace (24.4 KB per sample point) so that srf_render_rays_backward
                                        does not recompute the forward.  Outputs are bit-identical with and without it. */

@@ -47,24 +47,37 @@ def taps_2d(coords, norm_size, H, W):
     return out
 
 
-def mlp_forward_saved(params, z, x, n_blocks=3):
-    """resnetfc.py:133-164 in float64 keeping what the backward needs."""
+def tf32_trunc(a):
+    """Operand rounding of tcgen05 kind::tf32: the float32 value with its low 13 mantissa bits dropped."""
+    u = np.ascontiguousarray(a, dtype=f32).view(np.uint32) & np.uint32(0xFFFFE000)
+    return u.view(f32).astype(f64)
+
+
+def _mm(a, b, tf32):
+    """a @ b in float64; tf32=True emulates the tensor-core mode of csrc/gemm_tf32.cu (operands truncated to tf32,
+    products and sums exact/float32-accumulated on the device -- float64 here)."""
+    return (tf32_trunc(a) @ tf32_trunc(b)) if tf32 else (a @ b)
+
+
+def mlp_forward_saved(params, z, x, n_blocks=3, tf32=False):
+    """resnetfc.py:133-164 in float64 keeping what the backward needs.  tf32: the GEMMs the CUDA tf32 mode runs on tensor
+    cores (everything except lin_in / lin_out) use truncated operands."""
     P = {k: v.astype(f64) for k, v in params.items()}
     z, x = z.astype(f64), x.astype(f64)
     h = x @ P["lin_in.weight"].T + P["lin_in.bias"]
     saved = []
     for b in range(n_blocks):
-        pre = h + z @ P["lin_z.%d.weight" % b].T + P["lin_z.%d.bias" % b]
-        net = np.maximum(pre, 0) @ P["blocks.%d.fc_0.weight" % b].T + P["blocks.%d.fc_0.bias" % b]
-        h = pre + np.maximum(net, 0) @ P["blocks.%d.fc_1.weight" % b].T + P["blocks.%d.fc_1.bias" % b]
+        pre = h + _mm(z, P["lin_z.%d.weight" % b].T, tf32) + P["lin_z.%d.bias" % b]
+        net = _mm(np.maximum(pre, 0), P["blocks.%d.fc_0.weight" % b].T, tf32) + P["blocks.%d.fc_0.bias" % b]
+        h = pre + _mm(np.maximum(net, 0), P["blocks.%d.fc_1.weight" % b].T, tf32) + P["blocks.%d.fc_1.bias" % b]
         saved.append((pre, net))
     out = np.maximum(h, 0) @ P["lin_out.weight"].T + P["lin_out.bias"]
     return out, saved, h, P
 
 
-def mlp_backward(params, z, x, g_out, n_blocks=3):
+def mlp_backward(params, z, x, g_out, n_blocks=3, tf32=False):
     """-> (dict of parameter gradients, dz (n, d_latent))."""
-    out, saved, h3, P = mlp_forward_saved(params, z, x, n_blocks)
+    out, saved, h3, P = mlp_forward_saved(params, z, x, n_blocks, tf32)
     z64, x64 = z.astype(f64), x.astype(f64)
     g = {}
     g_out = g_out.astype(f64)
@@ -74,15 +87,15 @@ def mlp_backward(params, z, x, g_out, n_blocks=3):
     dz = np.zeros_like(z64)
     for b in reversed(range(n_blocks)):
         pre, net = saved[b]
-        g["blocks.%d.fc_1.weight" % b] = dh.T @ np.maximum(net, 0)
+        g["blocks.%d.fc_1.weight" % b] = _mm(dh.T, np.maximum(net, 0), tf32)
         g["blocks.%d.fc_1.bias" % b] = dh.sum(0)
-        dnet = (dh @ P["blocks.%d.fc_1.weight" % b]) * (net > 0)
-        g["blocks.%d.fc_0.weight" % b] = dnet.T @ np.maximum(pre, 0)
+        dnet = _mm(dh, P["blocks.%d.fc_1.weight" % b], tf32) * (net > 0)
+        g["blocks.%d.fc_0.weight" % b] = _mm(dnet.T, np.maximum(pre, 0), tf32)
         g["blocks.%d.fc_0.bias" % b] = dnet.sum(0)
-        dpre = dh + (dnet @ P["blocks.%d.fc_0.weight" % b]) * (pre > 0)
-        g["lin_z.%d.weight" % b] = dpre.T @ z64
+        dpre = dh + _mm(dnet, P["blocks.%d.fc_0.weight" % b], tf32) * (pre > 0)
+        g["lin_z.%d.weight" % b] = _mm(dpre.T, z64, tf32)
         g["lin_z.%d.bias" % b] = dpre.sum(0)
-        dz += dpre @ P["lin_z.%d.weight" % b]
+        dz += _mm(dpre, P["lin_z.%d.weight" % b], tf32)
         dh = dpre
     g["lin_in.weight"] = dh.T @ x64
     g["lin_in.bias"] = dh.sum(0)
@@ -105,7 +118,7 @@ def scatter_latent_grad(dz, coords, x_rgb, sphere_W, sphere_H, grads):
         off += C
 
 
-def render_backward(orc: "so.OracleRenderer", K, T, x_rgb, pixels, noise_u, noise_n, cot: dict):
+def render_backward(orc: "so.OracleRenderer", K, T, x_rgb, pixels, noise_u, noise_n, cot: dict, tf32: bool = False):
     """One chunk (all rays) of render_rays_batch, forward + backward.  cot: cotangents for GRAD_KEYS (missing = 0).
     Returns dict(out=forward outputs, g_main=..., g_gauss=... parameter grads, g_pyr={key: (C,H,W)}, graw_main, graw_gauss)."""
     cfg = orc.cfg
@@ -129,7 +142,8 @@ def render_backward(orc: "so.OracleRenderer", K, T, x_rgb, pixels, noise_u, nois
         return coords, z, x
 
     gp_coords, gp_lat, gp_x = inputs_of(gpts, G)
-    g_raw = so.resnetfc(orc.pg, gp_lat, gp_x).reshape(R, G, 2)
+    fwd = (lambda P_, z_, x_: mlp_forward_saved(P_, z_, x_, tf32=True)[0].astype(f32)) if tf32 else so.resnetfc
+    g_raw = fwd(orc.pg, gp_lat, gp_x).reshape(R, G, 2)
     pre_mean = (m0[None, :] + g_raw[:, :, 0]).astype(f32)
     pre_std = (g_raw[:, :, 1] + f32(cfg.std)).astype(f32)
     means = (np.maximum(pre_mean, 0) + orc.add_const).astype(f32)
@@ -146,7 +160,7 @@ def render_backward(orc: "so.OracleRenderer", K, T, x_rgb, pixels, noise_u, nois
     pts = np.take_along_axis(pts, order[:, :, None], 1)
     S = t.shape[1]
     mp_coords, mp_lat, mp_x = inputs_of(pts.reshape(-1, 3), S)
-    m_raw = so.resnetfc(orc.pm, mp_lat, mp_x)
+    m_raw = fwd(orc.pm, mp_lat, mp_x)
     colors = so.sigmoid(m_raw[:, :3]).reshape(R, S, 3)
     sigma = so.softplus(m_raw[:, 3] - f32(1)).reshape(R, S)
     ro = orc.render_depth_and_color(sigma, t, zc, colors)
@@ -215,8 +229,8 @@ def render_backward(orc: "so.OracleRenderer", K, T, x_rgb, pixels, noise_u, nois
     dsoft = np.where(x3 > 20.0, 1.0, 1.0 / (1.0 + np.exp(-x3)))
     graw_main = np.concatenate([(g_col * col * (1 - col)).reshape(-1, 3), (g_sigma.reshape(-1) * dsoft)[:, None]], axis=1)
     # MLPs + feature maps
-    g_main, dz_main, _ = mlp_backward(orc.pm, mp_lat, mp_x, graw_main)
-    g_gauss, dz_gauss, _ = mlp_backward(orc.pg, gp_lat, gp_x, graw_gauss)
+    g_main, dz_main, _ = mlp_backward(orc.pm, mp_lat, mp_x, graw_main, tf32=tf32)
+    g_gauss, dz_gauss, _ = mlp_backward(orc.pg, gp_lat, gp_x, graw_gauss, tf32=tf32)
     g_pyr = {k: np.zeros(v.shape, f64) for k, v in x_rgb.items()}
     scatter_latent_grad(dz_main, mp_coords, x_rgb, cfg.sphere_W, cfg.sphere_H, g_pyr)
     scatter_latent_grad(dz_gauss, gp_coords, x_rgb, cfg.sphere_W, cfg.sphere_H, g_pyr)

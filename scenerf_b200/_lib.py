@@ -17,6 +17,7 @@ PREC_FP16_TC = 1
 FLAG_SKIP_ZERO_CHUNKS = 1
 FLAG_HIDDEN_FP16 = 2
 FLAG_SAVE_ACTIVATIONS = 4
+FLAG_TF32_MATMUL = 8
 PYR_FP32 = 0
 PYR_FP16 = 1
 

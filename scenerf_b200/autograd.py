@@ -58,6 +58,8 @@ class RenderRaysFunction(torch.autograd.Function):
         cfg = r._config(cam_K, T)
         if r.save_activations:
             cfg.flags |= _lib.FLAG_SAVE_ACTIVATIONS       # the backward reads the pre-activations instead of recomputing them
+        if r.tf32_matmul:
+            cfg.flags |= _lib.FLAG_SAVE_ACTIVATIONS | _lib.FLAG_TF32_MATMUL
         pyr = r._pack_pyramid(dict(zip(SCALE_KEYS, maps)))
         if pyr.format != _lib.PYR_FP32:
             raise RuntimeError("training needs a renderer built with precision='fp32'")
@@ -126,7 +128,10 @@ class TrainableRenderer:
     """`render_rays_batch` with the reference's signature whose outputs carry gradients to `mlp`, `mlp_gaussian`
     (any nn.Module / dict with the ResnetFC parameter names) and to the five maps of `x_rgb`."""
 
-    def __init__(self, hp: dict, mlp, mlp_gaussian, device="cuda:0", rng: str = "torch", save_activations: bool = True):
+    def __init__(self, hp: dict, mlp, mlp_gaussian, device="cuda:0", rng: str = "torch", save_activations: bool = True,
+                 matmul: str = "fp32"):
+        if matmul not in ("fp32", "tf32"):
+            raise ValueError("matmul must be 'fp32' (strict SIMT) or 'tf32' (tcgen05 tensor cores)")
         state = lambda m: dict(m.named_parameters()) if hasattr(m, "named_parameters") else dict(m)
         self.mlp, self.mlp_gaussian = mlp, mlp_gaussian
         self._state = state
@@ -136,6 +141,9 @@ class TrainableRenderer:
         # True: keep the ResnetFC pre-activations of the forward (24.4 KB per sample point) for the backward;
         # False: recompute them chunk by chunk in the backward (less memory, ~25 % more arithmetic)
         self.renderer.save_activations = bool(save_activations)
+        # "tf32": the GEMMs of the training forward and of the backward run as tcgen05 kind::tf32 (float32 storage, 10-bit
+        # mantissa operands) -- several times faster, not bit-compatible with the strict mode
+        self.renderer.tf32_matmul = matmul == "tf32"
 
     def render_rays_batch(self, cam_K, T_source2infer, x_rgb, depth_window=100, T_cam2velo=None, sampled_pixels=None,
                           ray_batch_size=128, *, noise=None):

@@ -155,7 +155,8 @@ int run_mlp(const srf::DevParams& p, int precision, int flags, const srf_mlp_wei
   int l;
   const int pass = (w.d_out == 4) ? 1 : 0;
   prof_record(2 * pass, st);
-  if (precision == SRF_PREC_FP32 && saved) l = srf::run_point_mlp_forward_save(p, w, pts, viewdir, n, n_per, raw, dbg, saved, st);
+  if (precision == SRF_PREC_FP32 && saved)
+    l = srf::run_point_mlp_forward_save(p, w, pts, viewdir, n, n_per, raw, dbg, saved, (flags & SRF_FLAG_TF32_MATMUL) ? 1 : 0, ws, ws_bytes, st);
   else if (precision == SRF_PREC_FP32) l = srf::run_point_mlp_simt(p, w, pts, viewdir, n, n_per, raw, dbg, ws, ws_bytes, st);
   else l = srf::run_point_mlp_tc(p, w, pts, viewdir, n, n_per, raw, dbg, flags, ws, ws_bytes, st);
   if (l < 0) return fail(SRF_E_WORKSPACE, "point-MLP workspace too small (%zu bytes)", ws_bytes);
@@ -469,17 +470,21 @@ int srf_render_rays_backward(const srf_config* cfg, const srf_pyramid* pyr, cons
   float* graw_gauss = a.take<float>((size_t)R * G * 2);
   const size_t mlp_ws_bytes = workspace_bytes - a.off - 2048;
   void* mlp_ws = a.take<unsigned char>(mlp_ws_bytes);
+  const int tf32 = (cfg->flags & SRF_FLAG_TF32_MATMUL) ? 1 : 0;
+  if (tf32 && !fw.saved_main)
+    return fail(SRF_E_INVALID, "srf_render_rays_backward: SRF_FLAG_TF32_MATMUL needs SRF_FLAG_SAVE_ACTIVATIONS (forward and backward must "
+                               "see the same activations)");
   srf::launch_ray_backward(p, R, fw.raw, fw.t_sorted, fw.unit, fw.gauss_raw, noise_n_dev, *fwd_out, *grad_out, graw_main,
                            graw_gauss, st);
   ++g_launches;
   if (int rc = check_cuda("ray_backward")) return rc;
   int l = srf::run_point_mlp_backward_simt(p, *w_main, *grad_main, grad_pyr_chw, fw.pts, fw.viewdir, R * S, S, graw_main, fw.saved_main,
-                                           mlp_ws, mlp_ws_bytes, st);
+                                           tf32, mlp_ws, mlp_ws_bytes, st);
   if (l < 0) return fail(SRF_E_WORKSPACE, "srf_render_rays_backward: MLP backward workspace too small");
   g_launches += l;
   if (int rc = check_cuda("main MLP backward")) return rc;
   l = srf::run_point_mlp_backward_simt(p, *w_gauss, *grad_gauss, grad_pyr_chw, fw.gauss_pts, fw.viewdir, R * G, G, graw_gauss,
-                                       fw.saved_gauss, mlp_ws, mlp_ws_bytes, st);
+                                       fw.saved_gauss, tf32, mlp_ws, mlp_ws_bytes, st);
   if (l < 0) return fail(SRF_E_WORKSPACE, "srf_render_rays_backward: MLP backward workspace too small");
   g_launches += l;
   return check_cuda("gaussian MLP backward");

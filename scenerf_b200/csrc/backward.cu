@@ -198,6 +198,10 @@ struct GemmOpt {
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
   const int* skip = nullptr;
 };
+// SRF_FLAG_TF32_MATMUL: NT GEMMs without operand ReLU go to the tcgen05 kind::tf32 kernel (gemm_tf32.cu); the callers
+// below arrange their operands accordingly (ReLU'd / transposed copies).  Set per call by the run_* entry points.
+static thread_local bool g_tf32 = false;
+
 template <bool AT, bool BT, bool RA, bool RB>
 static void gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const GemmOpt& o,
                  cudaStream_t st) {
@@ -206,6 +210,7 @@ static void gemm(const float* A, int lda, const float* B, int ldb, float* C, int
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   g.bias = o.bias; g.mask = o.mask; g.ldm = o.ldm; g.R = o.R; g.ldr = o.ldr; g.accumulate = o.accumulate;
   g.splitk_ws = o.splitk_ws; g.splitk_ws_floats = o.splitk_ws_floats; g.skip_if_zero = o.skip;
+  if (g_tf32 && !AT && BT && !RA && !RB && launch_gemm_tf32(g, st) == 0) return;
   launch_gemm(g, st);
 }
 
@@ -240,6 +245,42 @@ colsum_final_kernel(const float* __restrict__ part, int N, float* __restrict__ g
 static void colsum(const float* dY, int ld, int M, int N, float* gb, float* scratch, cudaStream_t st) {
   colsum_partial_kernel<<<dim3((N + 31) / 32, kColSegs), 256, 0, st>>>(dY, ld, M, N, scratch);
   colsum_final_kernel<<<(N + 255) / 256, 256, 0, st>>>(scratch, N, gb);
+}
+
+// dst[c][r] = relu?(src[r][c])   (rows x cols -> cols x rows; dst row stride ldd >= rows)
+template <bool RELU>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ src, int lds, int rows, int cols, float* __restrict__ dst, int ldd) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + i * 8, c = c0 + tx;
+    float v = (r < rows && c < cols) ? src[(size_t)r * lds + c] : 0.f;
+    if (RELU) v = fmaxf(v, 0.f);
+    t[ty + i * 8][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, r = r0 + tx;
+    if (c < cols && r < rows) dst[(size_t)c * ldd + r] = t[tx][ty + i * 8];
+  }
+}
+template <bool RELU>
+static void transpose(const float* src, int lds, int rows, int cols, float* dst, int ldd, cudaStream_t st) {
+  transpose_kernel<RELU><<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, st>>>(src, lds, rows, cols, dst, ldd);
+}
+__global__ void __launch_bounds__(256) relu_kernel(const float4* __restrict__ src, float4* __restrict__ dst, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = src[i];
+  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+  dst[i] = v;
+}
+static void relu_copy(const float* src, float* dst, size_t n, cudaStream_t st) {
+  relu_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), n / 4);
 }
 
 // dh[m][c] = (h3[m][c] > 0) ? sum_o g[m][o] * Wout[o][c] : 0        (lin_out backward w.r.t. its input)
@@ -287,7 +328,10 @@ static inline int xin_ld_b(int d_latent) { return ((d_latent + kDX + 31) / 32) *
 
 size_t mlp_backward_workspace_bytes(int d_latent, int n_points) {
   const size_t m = (size_t)(n_points < kChunkB ? n_points : kChunkB);
-  return m * ((size_t)2 * xin_ld_b(d_latent) + 10 * kHidden) * sizeof(float) + kSplitKFloats * sizeof(float) + 512;
+  // + tf32 mode: transposed copies (2 x [512][m], X^T [ld][m]) and the transposed weights (6 x 512x512, 3 x 512 x d_latent)
+  const size_t tf32_extra = ((size_t)2 * kHidden * (m + 4) + (size_t)xin_ld_b(d_latent) * (m + 4) + (size_t)6 * kHidden * kHidden +
+                             (size_t)3 * kHidden * d_latent) * sizeof(float);
+  return m * ((size_t)2 * xin_ld_b(d_latent) + 10 * kHidden) * sizeof(float) + kSplitKFloats * sizeof(float) + 512 + tf32_extra;
 }
 
 // Activations of the float32 forward that the backward needs, for ALL points of a pass (SRF_FLAG_SAVE_ACTIVATIONS): the
@@ -310,8 +354,10 @@ static SavedActs saved_view(void* base, int d_latent, int n) {
 
 // resnetfc.py:133-164 for m points keeping the pre-activations: PRE[b] = h + lin_z_b(z), NET[b] = fc_0(relu(PRE[b])),
 // H3 = h after block 2.  Returns launches.
+// relu_scratch: m x 512 floats, used only in tf32 mode (the tensor-core GEMM takes its A operand as stored, so the
+// ReLU'd activations are materialised first).
 static int forward_chunk(const DevParams& p, const srf_mlp_weights& w, const float* X, int ld, float* const* PRE, float* const* NET,
-                         float* H3, int m, const int* scale_any, cudaStream_t st) {
+                         float* H3, int m, const int* scale_any, float* relu_scratch, cudaStream_t st) {
   const int H = kHidden, DL = p.d_latent;
   GemmOpt o;
   o.bias = w.lin_in_b;
@@ -324,10 +370,20 @@ static int forward_chunk(const DevParams& p, const srf_mlp_weights& w, const flo
       else { o.accumulate = 1; o.skip = scale_any + s; }
       gemm<false, true, false, false>(X + p.ch_off[s], ld, w.lin_z_w[b] + p.ch_off[s], DL, PRE[b], H, m, H, p.C[s], o, st);
     }
-    o = GemmOpt(); o.bias = w.fc0_b[b];
-    gemm<false, true, true, false>(PRE[b], H, w.fc0_w[b], H, NET[b], H, m, H, H, o, st);                       // net = fc_0(relu(pre))
-    o = GemmOpt(); o.bias = w.fc1_b[b]; o.R = PRE[b]; o.ldr = H;
-    gemm<false, true, true, false>(NET[b], H, w.fc1_w[b], H, H3, H, m, H, H, o, st);                           // h = pre + fc_1(relu(net))
+    if (g_tf32 && relu_scratch) {
+      relu_copy(PRE[b], relu_scratch, (size_t)m * H, st);
+      o = GemmOpt(); o.bias = w.fc0_b[b];
+      gemm<false, true, false, false>(relu_scratch, H, w.fc0_w[b], H, NET[b], H, m, H, H, o, st);              // net = fc_0(relu(pre))
+      relu_copy(NET[b], relu_scratch, (size_t)m * H, st);
+      o = GemmOpt(); o.bias = w.fc1_b[b]; o.R = PRE[b]; o.ldr = H;
+      gemm<false, true, false, false>(relu_scratch, H, w.fc1_w[b], H, H3, H, m, H, H, o, st);                  // h = pre + fc_1(relu(net))
+      launches += 2;
+    } else {
+      o = GemmOpt(); o.bias = w.fc0_b[b];
+      gemm<false, true, true, false>(PRE[b], H, w.fc0_w[b], H, NET[b], H, m, H, H, o, st);                     // net = fc_0(relu(pre))
+      o = GemmOpt(); o.bias = w.fc1_b[b]; o.R = PRE[b]; o.ldr = H;
+      gemm<false, true, true, false>(NET[b], H, w.fc1_w[b], H, H3, H, m, H, H, o, st);                         // h = pre + fc_1(relu(net))
+    }
     launches += kScales + 2;
   }
   return launches;
@@ -335,8 +391,12 @@ static int forward_chunk(const DevParams& p, const srf_mlp_weights& w, const flo
 
 // Training forward of one pass: same arithmetic as run_point_mlp_simt (bit-identical raw outputs), activations kept.
 int run_point_mlp_forward_save(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n, int n_per,
-                               float* raw_out, int32_t* dbg_sphere, void* saved_base, cudaStream_t st) {
+                               float* raw_out, int32_t* dbg_sphere, void* saved_base, int tf32_matmul, void* scratch, size_t scratch_bytes,
+                               cudaStream_t st) {
   const int ld = xin_ld_b(p.d_latent), H = kHidden;
+  g_tf32 = tf32_matmul != 0;
+  float* relu_scratch = reinterpret_cast<float*>(scratch);
+  if (g_tf32 && scratch_bytes < (size_t)(n < kChunkB ? n : kChunkB) * H * sizeof(float)) return -1;
   const SavedActs a = saved_view(saved_base, p.d_latent, n);
   int launches = 0, chunk = 0;
   for (int p0 = 0; p0 < n; p0 += kChunkB, ++chunk) {
@@ -347,7 +407,7 @@ int run_point_mlp_forward_save(const DevParams& p, const srf_mlp_weights& w, con
     float* H3 = a.H3 + (size_t)p0 * H;
     int* flags = a.flags + chunk * 8;
     launch_build_xin(p, pts, viewdir, m, n_per, p0, X, ld, dbg_sphere, flags, st);
-    launches += 1 + forward_chunk(p, w, X, ld, PRE, NET, H3, m, flags, st);
+    launches += 1 + forward_chunk(p, w, X, ld, PRE, NET, H3, m, flags, relu_scratch, st);
     launch_lin_out(H3, w.lin_out_w, w.lin_out_b, raw_out + (size_t)p0 * w.d_out, m, w.d_out, st);
     ++launches;
   }
@@ -359,8 +419,9 @@ int run_point_mlp_forward_save(const DevParams& p, const srf_mlp_weights& w, con
 // Returns launches or -1.
 int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, const srf_mlp_weights& gw, float* const* grad_pyr_chw,
                                 const float* pts, const float* viewdir, int n, int n_per, const float* g_raw, const void* saved_base,
-                                void* workspace, size_t ws_bytes, cudaStream_t st) {
+                                int tf32_matmul, void* workspace, size_t ws_bytes, cudaStream_t st) {
   if (ws_bytes < mlp_backward_workspace_bytes(p.d_latent, n)) return -1;
+  g_tf32 = tf32_matmul != 0;
   const int ld = xin_ld_b(p.d_latent), H = kHidden, DL = p.d_latent;
   const size_t cap = (size_t)(n < kChunkB ? n : kChunkB);
   float* Xc = reinterpret_cast<float*>(workspace);
@@ -373,7 +434,21 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
   float* dN = q; q += cap * H;
   float* dP = q; q += cap * H;
   float* SK = q; q += kSplitKFloats;
-  int* flags_c = reinterpret_cast<int*>(q);
+  int* flags_c = reinterpret_cast<int*>(q); q += 128;
+  // tf32 mode scratch
+  const int mp = (int)((cap + 3) / 4 * 4);                 // row stride of the transposed activations (16-byte aligned rows)
+  float* Tt0 = q; q += (size_t)H * mp;                     // dY^T
+  float* Tt1 = q; q += (size_t)H * mp;                     // relu(X)^T
+  float* Xt = q; q += (size_t)ld * mp;                     // z^T (all latent columns)
+  float* WT0[3]; float* WT1[3]; float* WTZ[3];
+  for (int b = 0; b < 3; ++b) { WT0[b] = q; q += (size_t)H * H; WT1[b] = q; q += (size_t)H * H; WTZ[b] = q; q += (size_t)H * DL; }
+  if (g_tf32) {
+    for (int b = 0; b < 3; ++b) {                          // W^T so that dX = dY W becomes an NT product
+      transpose<false>(w.fc0_w[b], H, H, H, WT0[b], H, st);
+      transpose<false>(w.fc1_w[b], H, H, H, WT1[b], H, st);
+      transpose<false>(w.lin_z_w[b], DL, H, DL, WTZ[b], H, st);
+    }
+  }
   SavedActs sv;
   if (saved_base) sv = saved_view(const_cast<void*>(saved_base), p.d_latent, n);
   auto G = [](const float* c) { return const_cast<float*>(c); };
@@ -393,7 +468,7 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
     } else {
       // ---- forward recompute, keeping pre-activations (resnetfc.py:133-164) ----
       launch_build_xin(p, pts, viewdir, m, n_per, p0, X, ld, nullptr, scale_any, st);
-      launches += 1 + forward_chunk(p, w, X, ld, PRE, NET, H3, m, scale_any, st);
+      launches += 1 + forward_chunk(p, w, X, ld, PRE, NET, H3, m, scale_any, dN, st);
     }
     // ---- backward ----
     o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
@@ -401,6 +476,38 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
     colsum(g_out, w.d_out, m, w.d_out, G(gw.lin_out_b), SK, st);
     lin_out_dx_kernel<<<(m * H + 255) / 256, 256, 0, st>>>(g_out, w.d_out, w.lin_out_w, H3, dH, m);
     launches += 5;
+    if (g_tf32) {
+      // every product as NT on tensor cores: dW = (dY^T)(relu(X)^T)^T with K = m, dX = dY (W^T)^T
+      const int mq = (m + 3) / 4 * 4;
+      transpose<false>(X, ld, m, DL, Xt, mq, st);                                                              // z^T, once per chunk
+      for (int b = 2; b >= 0; --b) {
+        transpose<false>(dH, H, m, H, Tt0, mq, st);
+        transpose<true>(NET[b], H, m, H, Tt1, mq, st);
+        o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
+        gemm<false, true, false, false>(Tt0, mq, Tt1, mq, G(gw.fc1_w[b]), H, H, H, m, o, st);                  // gW_fc1 += dh^T relu(net)
+        colsum(dH, H, m, H, G(gw.fc1_b[b]), SK, st);
+        o = GemmOpt(); o.mask = NET[b]; o.ldm = H;
+        gemm<false, true, false, false>(dH, H, WT1[b], H, dN, H, m, H, H, o, st);                              // dnet = (dh W_fc1) * (net>0)
+        transpose<false>(dN, H, m, H, Tt0, mq, st);
+        transpose<true>(PRE[b], H, m, H, Tt1, mq, st);
+        o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
+        gemm<false, true, false, false>(Tt0, mq, Tt1, mq, G(gw.fc0_w[b]), H, H, H, m, o, st);                  // gW_fc0 += dnet^T relu(pre)
+        colsum(dN, H, m, H, G(gw.fc0_b[b]), SK, st);
+        o = GemmOpt(); o.mask = PRE[b]; o.ldm = H; o.R = dH; o.ldr = H;
+        gemm<false, true, false, false>(dN, H, WT0[b], H, dP, H, m, H, H, o, st);                              // dpre = dh + (dnet W_fc0) * (pre>0)
+        transpose<false>(dP, H, m, H, Tt0, mq, st);
+        for (int s = 0; s < kScales; ++s) {
+          o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats; o.skip = s ? scale_any + s : nullptr;
+          gemm<false, true, false, false>(Tt0, mq, Xt + (size_t)p.ch_off[s] * mq, mq, G(gw.lin_z_w[b]) + p.ch_off[s], DL, H, p.C[s], m, o, st);
+          o = GemmOpt(); o.accumulate = (b == 2) ? 0 : 1; o.skip = s ? scale_any + s : nullptr;
+          gemm<false, true, false, false>(dP, H, WTZ[b] + (size_t)p.ch_off[s] * H, H, dZ + p.ch_off[s], ld, m, p.C[s], H, o, st);
+        }
+        colsum(dP, H, m, H, G(gw.lin_z_b[b]), SK, st);
+        float* tmp = dH; dH = dP; dP = tmp;
+        launches += 21;
+      }
+      ++launches;
+    } else
     for (int b = 2; b >= 0; --b) {
       o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
       gemm<true, false, false, true>(dH, H, NET[b], H, G(gw.fc1_w[b]), H, H, H, m, o, st);                     // gW_fc1 += dh^T relu(net)

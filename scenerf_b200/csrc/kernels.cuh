@@ -70,10 +70,11 @@ void launch_lin_out(const float* Hh, const float* W, const float* bias, float* o
 size_t mlp_backward_workspace_bytes(int d_latent, int n_points);
 size_t mlp_saved_bytes(int d_latent, int n_points);            // activation store of one pass (SRF_FLAG_SAVE_ACTIVATIONS)
 int run_point_mlp_forward_save(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n, int n_per,
-                               float* raw_out, int32_t* dbg_sphere, void* saved_base, cudaStream_t st);
+                               float* raw_out, int32_t* dbg_sphere, void* saved_base, int tf32_matmul, void* scratch, size_t scratch_bytes,
+                               cudaStream_t st);
 int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, const srf_mlp_weights& gw, float* const* grad_pyr_chw,
                                 const float* pts, const float* viewdir, int n, int n_per, const float* g_raw, const void* saved_base,
-                                void* workspace, size_t ws_bytes, cudaStream_t st);
+                                int tf32_matmul, void* workspace, size_t ws_bytes, cudaStream_t st);
 void launch_ray_backward(const DevParams& p, int R, const float* raw, const float* t_sorted, const float* unit,
                          const float* gauss_raw, const float* noise_n, const srf_outputs& fwd, const srf_outputs& cot,
                          float* graw_main, float* graw_gauss, cudaStream_t st);

@@ -104,6 +104,7 @@ class B200Renderer:
         self.last_launches = 0
         self.last_backward_launches = 0
         self.save_activations = False
+        self.tf32_matmul = False
 
     # ------------------------------------------------------------------------------------------------------------
     @classmethod
