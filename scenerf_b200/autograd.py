@@ -170,11 +170,11 @@ class TrainableRenderer:
         return dict(zip(DICT_KEYS, outs))
 
 
-def patch_for_training(model, rng: str = "torch"):
+def patch_for_training(model, rng: str = "torch", matmul: str = "fp32"):
     """Route `model.render_rays_batch` of a reference SceneRF module through the differentiable B200 path: gradients
     reach model.mlp, model.mlp_gaussian and (through x_rgb) the image encoder.  Returns the TrainableRenderer."""
     base = B200Renderer.from_module(model, precision="fp32", rng=rng)
-    t = TrainableRenderer(base.hp, model.mlp, model.mlp_gaussian, device=base.device, rng=rng)
+    t = TrainableRenderer(base.hp, model.mlp, model.mlp_gaussian, device=base.device, rng=rng, matmul=matmul)
     if t.renderer.hp["dataset"] == "kitti":
         def render_rays_batch(cam_K, T_source2infer, x_rgb, depth_window=100, T_cam2velo=None, sampled_pixels=None,
                               ray_batch_size=128):
