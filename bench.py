@@ -143,7 +143,8 @@ def cpu_rays_per_sec(cfg, pix, pyramid, target_seconds=15.0, chunk=128):
     with ctx.Pool(workers, initializer=_cpu_init, initargs=(cfg, 0, blas)) as pool:
         rng = np.random.default_rng(0)
         sel = rng.permutation(pix.shape[0])
-        mk = lambda i: (np.ascontiguousarray(pix[sel[i * chunk:(i + 1) * chunk]]), i)
+        # chunk i of the shuffled rays; a workload smaller than the sample (config A: 1024 rays) wraps around
+        mk = lambda i: (np.ascontiguousarray(pix[sel[(i * chunk + np.arange(chunk)) % sel.shape[0]]]), i)
         t0 = time.perf_counter()
         pool.map(_cpu_chunk, [mk(i) for i in range(workers)])            # warm-up + calibration round
         t_round = time.perf_counter() - t0
