@@ -360,16 +360,25 @@ def run_train(args, rank, world, local):
     flop_fwd = R * flop_per_ray(cfg)
     flop_step = 4.0 * flop_fwd          # forward + recompute + dX GEMMs + dW GEMMs, each = one forward's FLOPs
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12          # 148 SMs x 128 FMA lanes x 2 x max clock
+    bound = "fp32 FMA (SIMT)"
+    if args.train_matmul == "tf32":
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        fp32_peak = float(peaks.get("bf16_tflops_sustained") or 1400.0) / 2.0      # kind::tf32 issues at half the kind::f16 rate
+        bound = "tensor (tcgen05 kind::tf32; peak = measured bf16 sustained / 2)"
     res = {"metric": "training rays/sec (render_rays_batch forward + backward, %d rays x %d samples per step)" % (R, cfg.S),
            "value": world * R / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "dtype": "f32" if args.train_matmul == "fp32" else "tf32 operands, f32 storage and accumulate",
            "data": "synthetic", "scaling": "weak", "higher_is_better": True,
            "forward_ms": fwd_ms, "backward_ms": bwd_ms, "loss": lv,
            "gpu_launches": int(t.renderer.last_launches + t.renderer.last_backward_launches),
-           "roofline": {"bound": "fp32 FMA (SIMT)", "achieved": 3.0 * flop_fwd / (ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+           "roofline": {"bound": bound, "achieved": 3.0 * flop_fwd / (ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                         "frac": 3.0 * flop_fwd / (ms * 1e-3) / 1e12 / fp32_peak,
                         "algorithmic_flop_per_step": 3.0 * flop_fwd, "dense_flop_per_step_with_recompute": flop_step,
-                        "note": "ALGORITHMIC flops (forward + dX + dW of the dense 2480-wide latent) / time; peak = 148 SMs x 128 lanes x "
+                        "note": "ALGORITHMIC flops (forward + dX + dW of the dense 2480-wide latent) / time; SIMT peak = 148 SMs x 128 lanes x "
                                 "2 FLOP x 1.965 GHz.  Not a utilisation figure: the lin_z K-segments of pyramid scales that no point of a "
                                 "chunk reaches (exact zeros, quirk Q2; typically 2240 of the 2480 latent columns) are skipped on the "
                                 "device, and the backward recomputes the forward per 9472-point chunk"}}

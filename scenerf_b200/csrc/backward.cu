@@ -197,6 +197,7 @@ struct GemmOpt {
   int accumulate = 0;
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
   const int* skip = nullptr;
+  const int* seg_flags = nullptr; int seg_mode = 0; const int* seg_off = nullptr;     // tf32 kernel: fused per-scale segments
 };
 // SRF_FLAG_TF32_MATMUL: NT GEMMs without operand ReLU go to the tcgen05 kind::tf32 kernel (gemm_tf32.cu); the callers
 // below arrange their operands accordingly (ReLU'd / transposed copies).  Set per call by the run_* entry points.
@@ -210,6 +211,7 @@ static void gemm(const float* A, int lda, const float* B, int ldb, float* C, int
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
   g.bias = o.bias; g.mask = o.mask; g.ldm = o.ldm; g.R = o.R; g.ldr = o.ldr; g.accumulate = o.accumulate;
   g.splitk_ws = o.splitk_ws; g.splitk_ws_floats = o.splitk_ws_floats; g.skip_if_zero = o.skip;
+  if (o.seg_flags) { g.seg_flags = o.seg_flags; g.seg_mode = o.seg_mode; for (int i = 0; i < 6; ++i) g.seg_off[i] = o.seg_off[i]; }
   if (g_tf32 && !AT && BT && !RA && !RB && launch_gemm_tf32(g, st) == 0) return;
   launch_gemm(g, st);
 }
@@ -364,6 +366,12 @@ static int forward_chunk(const DevParams& p, const srf_mlp_weights& w, const flo
   gemm<false, true, false, false>(X + DL, ld, w.lin_in_w, kDX, PRE[0], H, m, H, kDX, o, st);                   // h0 = lin_in(x)
   int launches = 1;
   for (int b = 0; b < 3; ++b) {
+    if (g_tf32 && relu_scratch) {                                                                              // one launch, dead scales' k-blocks skipped in the kernel
+      o = GemmOpt(); o.bias = w.lin_z_b[b]; o.R = (b == 0) ? PRE[0] : H3; o.ldr = H;
+      o.seg_flags = scale_any; o.seg_mode = 1; o.seg_off = p.ch_off;
+      gemm<false, true, false, false>(X, ld, w.lin_z_w[b], DL, PRE[b], H, m, H, DL, o, st);
+      launches -= kScales - 1;
+    } else
     for (int s = 0; s < kScales; ++s) {                                                                        // pre = h + lin_z(z), one K-segment per scale
       o = GemmOpt();
       if (s == 0) { o.bias = w.lin_z_b[b]; o.R = (b == 0) ? PRE[0] : H3; o.ldr = H; }
@@ -496,15 +504,15 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
         o = GemmOpt(); o.mask = PRE[b]; o.ldm = H; o.R = dH; o.ldr = H;
         gemm<false, true, false, false>(dN, H, WT0[b], H, dP, H, m, H, H, o, st);                              // dpre = dh + (dnet W_fc0) * (pre>0)
         transpose<false>(dP, H, m, H, Tt0, mq, st);
-        for (int s = 0; s < kScales; ++s) {
-          o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats; o.skip = s ? scale_any + s : nullptr;
-          gemm<false, true, false, false>(Tt0, mq, Xt + (size_t)p.ch_off[s] * mq, mq, G(gw.lin_z_w[b]) + p.ch_off[s], DL, H, p.C[s], m, o, st);
-          o = GemmOpt(); o.accumulate = (b == 2) ? 0 : 1; o.skip = s ? scale_any + s : nullptr;
-          gemm<false, true, false, false>(dP, H, WTZ[b] + (size_t)p.ch_off[s] * H, H, dZ + p.ch_off[s], ld, m, p.C[s], H, o, st);
-        }
+        // latent axis = output columns here: column tiles that lie in dead scales are skipped in the kernel (one launch each)
+        o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
+        o.seg_flags = scale_any; o.seg_mode = 2; o.seg_off = p.ch_off;
+        gemm<false, true, false, false>(Tt0, mq, Xt, mq, G(gw.lin_z_w[b]), DL, H, DL, m, o, st);                // gW_linz += dpre^T z
+        o = GemmOpt(); o.accumulate = (b == 2) ? 0 : 1; o.seg_flags = scale_any; o.seg_mode = 2; o.seg_off = p.ch_off;
+        gemm<false, true, false, false>(dP, H, WTZ[b], H, dZ, ld, m, DL, H, o, st);                             // dz (+)= dpre W_linz
         colsum(dP, H, m, H, G(gw.lin_z_b[b]), SK, st);
         float* tmp = dH; dH = dP; dP = tmp;
-        launches += 21;
+        launches += 14;
       }
       ++launches;
     } else

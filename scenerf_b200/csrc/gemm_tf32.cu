@@ -74,11 +74,21 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 // instruction descriptor: c_format F32 (1) at [4,6), a/b format TF32 (2) at [7,10) / [10,13), K-major, N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
+struct SegInfo { const int* flags; int mode; int off[6]; };
+// true when [lo, hi) of the latent axis touches only scales whose flag is 0
+__device__ __forceinline__ bool seg_dead(const SegInfo& sg, int lo, int hi) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s)
+    if (lo < sg.off[s + 1] && hi > sg.off[s] && sg.flags[s] != 0) return false;
+  return true;
+}
+
 __global__ void __launch_bounds__(kThreads)
 gemm_tf32_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* C, int ldc, int M, int N,
                     int K, const float* __restrict__ bias, const float* __restrict__ mask, int ldm, const float* R, int ldr,
-                    int accumulate, int k_per, const int* __restrict__ skip, int* err) {
+                    int accumulate, int k_per, const int* __restrict__ skip, const __grid_constant__ SegInfo sg, int* err) {
   if (skip && *skip == 0) return;
+  if (sg.mode == 2 && seg_dead(sg, blockIdx.x * kBN, min(N, (int)(blockIdx.x + 1) * kBN))) return;   // dead column tile
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t sA = base, sB = base + kStages * kTileBytes;
@@ -106,39 +116,49 @@ gemm_tf32_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
 
+  // K-segmented mode: k-blocks that lie entirely in dead scales are skipped by producer and issuer alike (same predicate,
+  // same order, so the ring stays in step); n_live = number of blocks actually streamed
+  int n_live = nk;
+  if (sg.mode == 1) {
+    n_live = 0;
+    for (int i = 0; i < nk; ++i) n_live += seg_dead(sg, kbeg + i * kBK, min(kend, kbeg + (i + 1) * kBK)) ? 0 : 1;
+  }
   if (warp == 0) {
     if (lane == 0) {
+      int j = 0;
       for (int i = 0; i < nk; ++i) {
-        const int s = i % kStages;
-        mbar_wait(bars + 8u * (kStages + s), (((uint32_t)(i / kStages)) & 1u) ^ 1u, err);
+        if (sg.mode == 1 && seg_dead(sg, kbeg + i * kBK, min(kend, kbeg + (i + 1) * kBK))) continue;
+        const int s = j % kStages;
+        mbar_wait(bars + 8u * (kStages + s), (((uint32_t)(j / kStages)) & 1u) ^ 1u, err);
         mbar_arrive_expect_tx(bars + 8u * s, 2 * kTileBytes);
         tma_load_2d(sA + s * kTileBytes, &tmA, kbeg + i * kBK, m0, bars + 8u * s);
         tma_load_2d(sB + s * kTileBytes, &tmB, kbeg + i * kBK, n0, bars + 8u * s);
+        ++j;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % kStages;
-        mbar_wait(bars + 8u * s, ((uint32_t)(i / kStages)) & 1u, err);
+      for (int j = 0; j < n_live; ++j) {
+        const int s = j % kStages;
+        mbar_wait(bars + 8u * s, ((uint32_t)(j / kStages)) & 1u, err);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int k4 = 0; k4 < kBK / 8; ++k4)
           umma_tf32(tmem, make_desc_sw128(sA + s * kTileBytes + k4 * 32), make_desc_sw128(sB + s * kTileBytes + k4 * 32), kIdesc,
-                    (i > 0 || k4 > 0) ? 1u : 0u);
+                    (j > 0 || k4 > 0) ? 1u : 0u);
         umma_commit(bars + 8u * (kStages + s));            // stage free once these MMAs have read it
       }
-      umma_commit(bars + 8u * (2 * kStages));              // accumulator complete
+      if (n_live > 0) umma_commit(bars + 8u * (2 * kStages));   // accumulator complete
     }
   } else {
     const int q = warp & 3;                                 // TMEM lane quarter this warp may read
     const int gm = m0 + q * 32 + lane;
-    if (nk > 0) mbar_wait(bars + 8u * (2 * kStages), 0, err);
+    if (n_live > 0) mbar_wait(bars + 8u * (2 * kStages), 0, err);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
     for (int c = 0; c < kBN / 32; ++c) {
       uint32_t v[32];
-      if (nk > 0) {
+      if (n_live > 0) {
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       } else {
@@ -175,10 +195,14 @@ gemm_tf32_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ part, int splits, float* __restrict__ C, int ldc, int M, int N, int accumulate,
-                     const int* __restrict__ skip) {
+                     const int* __restrict__ skip, const __grid_constant__ SegInfo sg) {
   if (skip && *skip == 0) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * N) return;
+  if (sg.mode == 2) {                                      // columns of a dead tile were never written by the GEMM
+    const int t0 = (i % N) / kBN * kBN;
+    if (seg_dead(sg, t0, min(N, t0 + kBN))) return;
+  }
   float v = 0.f;
   for (int z = 0; z < splits; ++z) v += part[(size_t)z * M * N + i];
   float* dst = C + (size_t)(i / N) * ldc + (i % N);
@@ -234,6 +258,9 @@ int launch_gemm_tf32(const GemmArgs& g, cudaStream_t st) {
   const size_t smem = 2 * tf32::kStages * tf32::kTileBytes + 1024 + 256;
   if (!attr) { cudaFuncSetAttribute(tf32::gemm_tf32_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
   dim3 grid((g.N + tf32::kBN - 1) / tf32::kBN, (g.M + tf32::kBM - 1) / tf32::kBM);
+  tf32::SegInfo sg;
+  sg.flags = g.seg_flags; sg.mode = g.seg_flags ? g.seg_mode : 0;
+  for (int i = 0; i < 6; ++i) sg.off[i] = g.seg_off[i];
   const int tiles = grid.x * grid.y;
   int splits = 1;
   if (g.splitk_ws && !g.bias && !g.mask && !g.R && tiles < 96 && g.K >= 1024) {
@@ -246,12 +273,12 @@ int launch_gemm_tf32(const GemmArgs& g, cudaStream_t st) {
     splits = (g.K + k_per - 1) / k_per;
     grid.z = splits;
     tf32::gemm_tf32_nt_kernel<<<grid, tf32::kThreads, smem, st>>>(tmA, tmB, g.splitk_ws, g.N, g.M, g.N, g.K, nullptr, nullptr, 0, nullptr, 0,
-                                                                  0, k_per, g.skip_if_zero, g_tf32_err);
+                                                                  0, k_per, g.skip_if_zero, sg, g_tf32_err);
     tf32::splitk_reduce_kernel<<<(g.M * g.N + 255) / 256, 256, 0, st>>>(g.splitk_ws, splits, g.C, g.ldc, g.M, g.N, g.accumulate,
-                                                                        g.skip_if_zero);
+                                                                        g.skip_if_zero, sg);
   } else {
     tf32::gemm_tf32_nt_kernel<<<grid, tf32::kThreads, smem, st>>>(tmA, tmB, g.C, g.ldc, g.M, g.N, g.K, g.bias, g.mask, g.ldm, g.R, g.ldr,
-                                                                  g.accumulate, g.K, g.skip_if_zero, g_tf32_err);
+                                                                  g.accumulate, g.K, g.skip_if_zero, sg, g_tf32_err);
   }
   return 0;
 }

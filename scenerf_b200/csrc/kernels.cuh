@@ -47,6 +47,10 @@ struct GemmArgs {
   float* C = nullptr; int ldc = 0; int M = 0, N = 0, K = 0;
   const float* bias = nullptr; const float* mask = nullptr; int ldm = 0; const float* R = nullptr; int ldr = 0; int accumulate = 0;
   const int* skip_if_zero = nullptr;   // device flag: when *flag == 0 the launch does nothing (an all-zero K-segment of the latent)
+  // tf32 kernel only: the latent axis (K when seg_mode == 1, N when seg_mode == 2) is the concatenation of the 5 pyramid
+  // scales [seg_off[s], seg_off[s+1]); k-blocks / column tiles that lie entirely in scales with seg_flags[s] == 0 are
+  // skipped on the device (their inputs are exact zeros / their outputs are never read).  One launch instead of five.
+  const int* seg_flags = nullptr; int seg_mode = 0; int seg_off[6] = {0, 0, 0, 0, 0, 0};
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;   // optional scratch: enables deterministic split-K for long-K, few-tile shapes
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t st);    // 0, or -1 for an operand-layout combination that is not instantiated
