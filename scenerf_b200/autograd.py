@@ -98,8 +98,14 @@ class RenderRaysFunction(torch.autograd.Function):
         tensors, fwd = saved[:49], dict(zip(DICT_KEYS, saved[49:]))
         maps, pm, pg = tensors[:5], tensors[5:27], tensors[27:49]
         w_main, w_gauss = _weights_struct(dict(zip(PARAM_KEYS, pm)), 4), _weights_struct(dict(zip(PARAM_KEYS, pg)), 2)
-        g_main = [torch.zeros_like(t) for t in pm]
-        g_gauss = [torch.zeros_like(t) for t in pg]
+        # one zero-filled slab for the 44 parameter gradients (one memset instead of 44), views handed to autograd
+        sizes = [t.numel() for t in pm] + [t.numel() for t in pg]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n + 3) // 4 * 4)          # keep every tensor 16-byte aligned (float4 / TMA paths)
+        slab = torch.zeros(offs[-1], dtype=torch.float32, device=r.device)
+        views = [slab[offs[i]:offs[i] + sizes[i]].view(t.shape) for i, t in enumerate(list(pm) + list(pg))]
+        g_main, g_gauss = views[:len(pm)], views[len(pm):]
         g_maps = [torch.zeros_like(t) for t in maps]
         if R:
             gw_main, gw_gauss = _weights_struct(dict(zip(PARAM_KEYS, g_main)), 4), _weights_struct(dict(zip(PARAM_KEYS, g_gauss)), 2)
