@@ -102,6 +102,8 @@ gemm_tf32_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (gridDim.z > 1) C += (size_t)blockIdx.z * M * ldc;
 
   if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");   // descriptor fetch off the first load's path
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int s = 0; s < kStages; ++s) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (kStages + s), 1); }
     mbar_init(bars + 8u * (2 * kStages), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
