@@ -59,3 +59,36 @@ def test_shard_range_covers_everything():
             assert sum(b - a for a, b, _ in spans) == n
             assert all(spans[i][1] == spans[i + 1][0] or spans[i + 1][0] == n for i in range(w - 1))
             assert len({p for _, _, p in spans}) == 1 and spans[0][2] * w >= n
+
+
+class _FakeLatticeRenderer:
+    """Stand-in with the two members density_lattice touches: a device and predict(..., "density")."""
+    device = torch.device("cpu")
+    last_launches = 1
+
+    def predict(self, mlp, pts, x_rgb, cam_K, T_cam2velo, viewdir, output_type):
+        dens = pts[..., 0] * 0.5 + pts[..., 1] * 3.0 + pts[..., 2] * 0.125
+        return dens, torch.stack([dens, dens * 2, dens * 3], dim=-1)
+
+
+def _lattice_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from scenerf_b200 import lattice
+        x, y, z = (-1.0, 0.5, 5), (-0.2, 0.1, 4), (0.2, 0.2, 7)          # 7 z-planes over 2 or 3 ranks: ragged slabs
+        r = _FakeLatticeRenderer()
+        full, fcol = lattice.density_lattice(r, None, None, x, y, z, cols_per_call=6, with_color=True)
+        shard, scol = lattice.density_lattice(r, None, None, x, y, z, cols_per_call=6, rank=rank, world=world, with_color=True)
+        ret[rank] = bool(torch.equal(full, shard) and torch.equal(fcol, scol) and tuple(shard.shape) == (5, 4, 7))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_density_lattice_z_slabs_equal_unsharded(world):
+    """z-slab sharding + all-gather + reassembly of scenerf_b200.lattice on CPU over gloo."""
+    ret = mp.Manager().dict()
+    mp.spawn(_lattice_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)

@@ -206,3 +206,31 @@ def test_sweep_pose_sharded_two_gpus():
            "--master-port", "29731", os.path.join(here, "_sweep_dist_worker.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "SWEEP_DIST_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_volume_merge_rule_on_the_oracle(g):
+    """The fold rule behind srf_tsdf_merge, on the CPU oracle: fusing contiguous pose ranges separately and folding the later
+    volume into the earlier one (keep A where |A| < |B|, weights add) reproduces the sequential integration -- distances and
+    weights exactly; colours except on float32-exact distance ties (see csrc/image_ops.cu)."""
+    inv = np.linalg.inv(g["T_velo2cam"])
+    frames = []
+    for i in range(N_POSES):
+        d, c = so.to_images(g["depth_rays%d" % i], g["color_rays%d" % i], (61, 19), (244, 74), 4)
+        frames.append((so.png_roundtrip(c), d, inv @ g["poses"][i].astype(np.float64)))
+
+    def fuse(idx):
+        v = TSDFVolumeOracle(g["vol_bnds"], 0.2, 10)
+        for i in idx:
+            v.integrate(frames[i][0], frames[i][1], g["K"], frames[i][2], 1.0)
+        return v
+    seq = fuse(range(N_POSES))
+    for cut in (2, 3):
+        a, b = fuse(range(cut)), fuse(range(cut, N_POSES))
+        t, w, c = np.full_like(seq.tsdf, 255), np.zeros_like(seq.tsdf), np.zeros_like(seq.tsdf)
+        for p in (a, b):
+            obs = p.weight != 0
+            take = obs & ~(np.abs(t) < np.abs(p.tsdf))
+            w = w + np.where(obs, p.weight, 0)
+            t, c = np.where(take, p.tsdf, t), np.where(take, p.color, c)
+        assert np.array_equal(t, seq.tsdf) and np.array_equal(w, seq.weight)
+        assert (c != seq.color).mean() <= 1e-4
