@@ -247,6 +247,7 @@ colsum_final_kernel(const float* __restrict__ part, int N, float* __restrict__ g
 static void colsum(const float* dY, int ld, int M, int N, float* gb, float* scratch, cudaStream_t st) {
   colsum_partial_kernel<<<dim3((N + 31) / 32, kColSegs), 256, 0, st>>>(dY, ld, M, N, scratch);
   colsum_final_kernel<<<(N + 255) / 256, 256, 0, st>>>(scratch, N, gb);
+  launch_counter() += 2;
 }
 
 // dst[c][r] = relu?(src[r][c])   (rows x cols -> cols x rows; dst row stride ldd >= rows)
@@ -273,6 +274,7 @@ transpose_kernel(const float* __restrict__ src, int lds, int rows, int cols, flo
 template <bool RELU>
 static void transpose(const float* src, int lds, int rows, int cols, float* dst, int ldd, cudaStream_t st) {
   transpose_kernel<RELU><<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, st>>>(src, lds, rows, cols, dst, ldd);
+  ++launch_counter();
 }
 __global__ void __launch_bounds__(256) relu_kernel(const float4* __restrict__ src, float4* __restrict__ dst, size_t n4) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(256) relu_kernel(const float4* __restrict__ sr
 }
 static void relu_copy(const float* src, float* dst, size_t n, cudaStream_t st) {
   relu_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), n / 4);
+  ++launch_counter();
 }
 
 // dh[m][c] = (h3[m][c] > 0) ? sum_o g[m][o] * Wout[o][c] : 0        (lin_out backward w.r.t. its input)
@@ -355,22 +358,20 @@ static SavedActs saved_view(void* base, int d_latent, int n) {
 }
 
 // resnetfc.py:133-164 for m points keeping the pre-activations: PRE[b] = h + lin_z_b(z), NET[b] = fc_0(relu(PRE[b])),
-// H3 = h after block 2.  Returns launches.
+// H3 = h after block 2.
 // relu_scratch: m x 512 floats, used only in tf32 mode (the tensor-core GEMM takes its A operand as stored, so the
 // ReLU'd activations are materialised first).
-static int forward_chunk(const DevParams& p, const srf_mlp_weights& w, const float* X, int ld, float* const* PRE, float* const* NET,
+static void forward_chunk(const DevParams& p, const srf_mlp_weights& w, const float* X, int ld, float* const* PRE, float* const* NET,
                          float* H3, int m, const int* scale_any, float* relu_scratch, cudaStream_t st) {
   const int H = kHidden, DL = p.d_latent;
   GemmOpt o;
   o.bias = w.lin_in_b;
   gemm<false, true, false, false>(X + DL, ld, w.lin_in_w, kDX, PRE[0], H, m, H, kDX, o, st);                   // h0 = lin_in(x)
-  int launches = 1;
   for (int b = 0; b < 3; ++b) {
     if (g_tf32 && relu_scratch) {                                                                              // one launch, dead scales' k-blocks skipped in the kernel
       o = GemmOpt(); o.bias = w.lin_z_b[b]; o.R = (b == 0) ? PRE[0] : H3; o.ldr = H;
       o.seg_flags = scale_any; o.seg_mode = 1; o.seg_off = p.ch_off;
       gemm<false, true, false, false>(X, ld, w.lin_z_w[b], DL, PRE[b], H, m, H, DL, o, st);
-      launches -= kScales - 1;
     } else
     for (int s = 0; s < kScales; ++s) {                                                                        // pre = h + lin_z(z), one K-segment per scale
       o = GemmOpt();
@@ -385,16 +386,13 @@ static int forward_chunk(const DevParams& p, const srf_mlp_weights& w, const flo
       relu_copy(NET[b], relu_scratch, (size_t)m * H, st);
       o = GemmOpt(); o.bias = w.fc1_b[b]; o.R = PRE[b]; o.ldr = H;
       gemm<false, true, false, false>(relu_scratch, H, w.fc1_w[b], H, H3, H, m, H, H, o, st);                  // h = pre + fc_1(relu(net))
-      launches += 2;
     } else {
       o = GemmOpt(); o.bias = w.fc0_b[b];
       gemm<false, true, true, false>(PRE[b], H, w.fc0_w[b], H, NET[b], H, m, H, H, o, st);                     // net = fc_0(relu(pre))
       o = GemmOpt(); o.bias = w.fc1_b[b]; o.R = PRE[b]; o.ldr = H;
       gemm<false, true, true, false>(NET[b], H, w.fc1_w[b], H, H3, H, m, H, H, o, st);                         // h = pre + fc_1(relu(net))
     }
-    launches += kScales + 2;
   }
-  return launches;
 }
 
 // Training forward of one pass: same arithmetic as run_point_mlp_simt (bit-identical raw outputs), activations kept.
@@ -406,7 +404,8 @@ int run_point_mlp_forward_save(const DevParams& p, const srf_mlp_weights& w, con
   float* relu_scratch = reinterpret_cast<float*>(scratch);
   if (g_tf32 && scratch_bytes < (size_t)(n < kChunkB ? n : kChunkB) * H * sizeof(float)) return -1;
   const SavedActs a = saved_view(saved_base, p.d_latent, n);
-  int launches = 0, chunk = 0;
+  const int c0 = launch_counter();
+  int chunk = 0;
   for (int p0 = 0; p0 < n; p0 += kChunkB, ++chunk) {
     const int m = (n - p0) < kChunkB ? (n - p0) : kChunkB;
     float* X = a.X + (size_t)p0 * ld;
@@ -415,11 +414,10 @@ int run_point_mlp_forward_save(const DevParams& p, const srf_mlp_weights& w, con
     float* H3 = a.H3 + (size_t)p0 * H;
     int* flags = a.flags + chunk * 8;
     launch_build_xin(p, pts, viewdir, m, n_per, p0, X, ld, dbg_sphere, flags, st);
-    launches += 1 + forward_chunk(p, w, X, ld, PRE, NET, H3, m, flags, relu_scratch, st);
+    forward_chunk(p, w, X, ld, PRE, NET, H3, m, flags, relu_scratch, st);
     launch_lin_out(H3, w.lin_out_w, w.lin_out_b, raw_out + (size_t)p0 * w.d_out, m, w.d_out, st);
-    ++launches;
   }
-  return launches;
+  return launch_counter() - c0;
 }
 
 // grads: same layout as the weights (accumulated into); pyramid grads CHW (accumulated into).  saved_base: activations of
@@ -462,7 +460,8 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
   auto G = [](const float* c) { return const_cast<float*>(c); };
   PyrGrad gp;
   for (int s = 0; s < kScales; ++s) gp.chw[s] = grad_pyr_chw[s];
-  int launches = 0, chunk = 0;
+  const int c0 = launch_counter();
+  int chunk = 0;
   for (int p0 = 0; p0 < n; p0 += kChunkB, ++chunk) {
     const int m = (n - p0) < kChunkB ? (n - p0) : kChunkB;
     const float* g_out = g_raw + (size_t)p0 * w.d_out;
@@ -476,14 +475,14 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
     } else {
       // ---- forward recompute, keeping pre-activations (resnetfc.py:133-164) ----
       launch_build_xin(p, pts, viewdir, m, n_per, p0, X, ld, nullptr, scale_any, st);
-      launches += 1 + forward_chunk(p, w, X, ld, PRE, NET, H3, m, scale_any, dN, st);
+      forward_chunk(p, w, X, ld, PRE, NET, H3, m, scale_any, dN, st);
     }
     // ---- backward ----
     o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
     gemm<true, false, false, true>(g_out, w.d_out, H3, H, G(gw.lin_out_w), H, w.d_out, H, m, o, st);           // gW_out += g^T relu(h3)
     colsum(g_out, w.d_out, m, w.d_out, G(gw.lin_out_b), SK, st);
     lin_out_dx_kernel<<<(m * H + 255) / 256, 256, 0, st>>>(g_out, w.d_out, w.lin_out_w, H3, dH, m);
-    launches += 5;
+    ++launch_counter();
     if (g_tf32) {
       // every product as NT on tensor cores: dW = (dY^T)(relu(X)^T)^T with K = m, dX = dY (W^T)^T
       const int mq = (m + 3) / 4 * 4;
@@ -512,9 +511,7 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
         gemm<false, true, false, false>(dP, H, WTZ[b], H, dZ, ld, m, DL, H, o, st);                             // dz (+)= dpre W_linz
         colsum(dP, H, m, H, G(gw.lin_z_b[b]), SK, st);
         float* tmp = dH; dH = dP; dP = tmp;
-        launches += 14;
       }
-      ++launches;
     } else
     for (int b = 2; b >= 0; --b) {
       o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
@@ -535,15 +532,14 @@ int run_point_mlp_backward_simt(const DevParams& p, const srf_mlp_weights& w, co
       }
       colsum(dP, H, m, H, G(gw.lin_z_b[b]), SK, st);
       float* tmp = dH; dH = dP; dP = tmp;                                                                      // dh <- dpre
-      launches += 16;
     }
     o = GemmOpt(); o.accumulate = 1; o.splitk_ws = SK; o.splitk_ws_floats = kSplitKFloats;
     gemm<true, false, false, false>(dH, H, X + DL, ld, G(gw.lin_in_w), kDX, H, kDX, m, o, st);                 // gW_in += dh^T x
     colsum(dH, H, m, H, G(gw.lin_in_b), SK, st);
     scatter_latent_kernel<<<(m + 7) / 8, 256, 0, st>>>(p, pts, m, p0, dZ, ld, gp);
-    launches += 5;
+    ++launch_counter();
   }
-  return launches;
+  return launch_counter() - c0;
 }
 
 void launch_ray_backward(const DevParams& p, int R, const float* raw, const float* t_sorted, const float* unit,

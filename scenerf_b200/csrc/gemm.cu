@@ -203,6 +203,11 @@ splitk_reduce_kernel(const float* __restrict__ part, int splits, float* __restri
   *dst = accumulate ? (*dst + v) : v;
 }
 
+int& launch_counter() {
+  static thread_local int c = 0;
+  return c;
+}
+
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <bool AT, bool BT, bool RA, bool RB>
@@ -232,7 +237,9 @@ static void dispatch(const GemmArgs& g, cudaStream_t st) {
       gemm128_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.splitk_ws, g.N, g.M, g.N, g.K, nullptr, nullptr, 0,
                                                            nullptr, 0, 0, k_per, g.skip_if_zero);
       splitk_reduce_kernel<<<(g.M * g.N + 255) / 256, 256, 0, st>>>(g.splitk_ws, splits, g.C, g.ldc, g.M, g.N, g.accumulate, g.skip_if_zero);
+      launch_counter() += 2;
     } else {
+      ++launch_counter();
       gemm128_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.M, g.N, g.K, g.bias, g.mask, g.ldm,
                                                            g.R, g.ldr, g.accumulate, g.K, g.skip_if_zero);
     }
@@ -252,7 +259,9 @@ static void dispatch(const GemmArgs& g, cudaStream_t st) {
       gemm64_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.splitk_ws, g.N, g.M, g.N, g.K, nullptr, nullptr, 0,
                                                           nullptr, 0, 0, k_per, g.skip_if_zero);
       splitk_reduce_kernel<<<(g.M * g.N + 255) / 256, 256, 0, st>>>(g.splitk_ws, splits, g.C, g.ldc, g.M, g.N, g.accumulate, g.skip_if_zero);
+      launch_counter() += 2;
     } else {
+      ++launch_counter();
       gemm64_kernel<AT, BT, RA, RB><<<grid, 256, 0, st>>>(g.A, g.lda, g.B, g.ldb, g.C, g.ldc, g.M, g.N, g.K, g.bias, g.mask, g.ldm,
                                                           g.R, g.ldr, g.accumulate, g.K, g.skip_if_zero);
     }

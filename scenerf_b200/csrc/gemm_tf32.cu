@@ -278,7 +278,9 @@ int launch_gemm_tf32(const GemmArgs& g, cudaStream_t st) {
                                                                   0, k_per, g.skip_if_zero, sg, g_tf32_err);
     tf32::splitk_reduce_kernel<<<(g.M * g.N + 255) / 256, 256, 0, st>>>(g.splitk_ws, splits, g.C, g.ldc, g.M, g.N, g.accumulate,
                                                                         g.skip_if_zero, sg);
+    launch_counter() += 2;
   } else {
+    ++launch_counter();
     tf32::gemm_tf32_nt_kernel<<<grid, tf32::kThreads, smem, st>>>(tmA, tmB, g.C, g.ldc, g.M, g.N, g.K, g.bias, g.mask, g.ldm, g.R, g.ldr,
                                                                   g.accumulate, g.K, g.skip_if_zero, sg, g_tf32_err);
   }

@@ -53,7 +53,10 @@ struct GemmArgs {
   const int* seg_flags = nullptr; int seg_mode = 0; int seg_off[6] = {0, 0, 0, 0, 0, 0};
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;   // optional scratch: enables deterministic split-K for long-K, few-tile shapes
 };
-int launch_gemm(const GemmArgs& g, cudaStream_t st);    // 0, or -1 for an operand-layout combination that is not instantiated
+int launch_gemm(const GemmArgs& g, cudaStream_t st);
+// per-thread count of kernels launched by the float32 / tf32 MLP paths (gemm.cu, gemm_tf32.cu, mlp_simt.cu, backward.cu);
+// the run_* entry points report the difference as their launch count (srf_last_launch_count)
+int& launch_counter();    // 0, or -1 for an operand-layout combination that is not instantiated
 
 // gemm_tf32.cu : the same contract on tensor cores (tcgen05 kind::tf32, float32 operands read in place); NT layout only
 // (at=false, bt=true, no operand ReLU).  Returns 0, or -1 when the shape cannot be expressed as TMA tensor maps.

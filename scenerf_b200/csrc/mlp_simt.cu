@@ -81,10 +81,12 @@ void launch_build_xin(const DevParams& p, const float* pts, const float* viewdir
                       int32_t* dbg_sphere, int* scale_any, cudaStream_t st) {
   if (scale_any) cudaMemsetAsync(scale_any, 0, kScales * sizeof(int), st);
   build_xin_kernel<<<(m + 7) / 8, 256, 0, st>>>(p, pts, viewdir, m, n_per, point0, X, ld, dbg_sphere, scale_any);
+  ++launch_counter();
 }
 
 void launch_lin_out(const float* Hh, const float* W, const float* bias, float* out, int M, int d_out, cudaStream_t st) {
   lin_out_kernel<<<(M + 7) / 8, 256, 0, st>>>(Hh, W, bias, out, M, d_out);
+  ++launch_counter();
 }
 
 size_t simt_workspace_bytes(int d_latent, int n_points) {
@@ -113,34 +115,27 @@ int run_point_mlp_simt(const DevParams& p, const srf_mlp_weights& w, const float
   float* Hh = X + (size_t)chunk_cap * ld;
   float* Nn = Hh + (size_t)chunk_cap * kHidden;
   int* scale_any = reinterpret_cast<int*>(Nn + (size_t)chunk_cap * kHidden);
-  int launches = 0;
+  const int c0 = launch_counter();
   for (int p0 = 0; p0 < n; p0 += kChunk) {
     const int m = (n - p0) < kChunk ? (n - p0) : kChunk;
     launch_build_xin(p, pts, viewdir, m, n_per, p0, X, ld, dbg_sphere, scale_any, st);
-    ++launches;
     // h = lin_in(x)                               (resnetfc.py:148)
     gemm<false>(X + p.d_latent, ld, w.lin_in_w, kDX, w.lin_in_b, Hh, m, kHidden, kDX, 0, st);
-    ++launches;
     for (int b = 0; b < SRF_NUM_BLOCKS; ++b) {
       // h = h + lin_z[b](z)                       (resnetfc.py:152-158)
       // one K-segment per pyramid scale; a scale no point of the chunk reaches is all zeros and is skipped on the device
       for (int s = 0; s < kScales; ++s) {
         gemm<false>(X + p.ch_off[s], ld, w.lin_z_w[b] + p.ch_off[s], p.d_latent, s == 0 ? w.lin_z_b[b] : nullptr, Hh, m, kHidden,
                     p.C[s], 1, st, s == 0 ? nullptr : scale_any + s);
-        ++launches;
       }
-      --launches;
       // net = fc_0(relu(h)); h = h + fc_1(relu(net))   (resnetfc.py:54-63)
       gemm<true>(Hh, kHidden, w.fc0_w[b], kHidden, w.fc0_b[b], Nn, m, kHidden, kHidden, 0, st);
       gemm<true>(Nn, kHidden, w.fc1_w[b], kHidden, w.fc1_b[b], Hh, m, kHidden, kHidden, 1, st);
-      launches += 3;
     }
     // out = lin_out(relu(h))                      (resnetfc.py:163)
-    lin_out_kernel<<<(m + 7) / 8, 256, 0, st>>>(Hh, w.lin_out_w, w.lin_out_b, raw_out + (size_t)p0 * w.d_out, m,
-                                                w.d_out);
-    ++launches;
+    launch_lin_out(Hh, w.lin_out_w, w.lin_out_b, raw_out + (size_t)p0 * w.d_out, m, w.d_out, st);
   }
-  return launches;
+  return launch_counter() - c0;
 }
 
 }  // namespace srf
