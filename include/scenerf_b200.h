@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SRF_ABI_VERSION 1
+#define SRF_ABI_VERSION 2
 #define SRF_NUM_SCALES 5   /* x_rgb keys "1_1","1_2","1_4","1_8","1_16" (unet2d_sphere.py:200-206) */
 #define SRF_NUM_BLOCKS 3   /* ResnetFC n_blocks (scenerf.py:100-114) */
 #define SRF_D_HIDDEN 512
@@ -41,7 +41,11 @@ enum srf_status {
 
 enum srf_precision {
   SRF_PREC_FP32 = 0, /* SIMT fp32 FMA everywhere: strict mode, matches the reference to float32 round-off */
-  SRF_PREC_FP16_TC = 1 /* tcgen05 tensor cores: fp16 operands, fp32 accumulate in TMEM */
+  SRF_PREC_FP16_TC = 1, /* tcgen05 tensor cores: fp16 operands, fp32 accumulate in TMEM ("fast mode") */
+  SRF_PREC_FP32_TC = 2  /* tcgen05 tensor cores at float32-grade accuracy: every fp32 operand is carried as an fp16
+                           hi/lo pair (22 mantissa bits), all four partial products accumulate in fp32 in TMEM.
+                           The precision-matched mode for the reference's fp32 sgemm (resnetfc.py:54-63,133-164);
+                           needs an SRF_PYR_FP32 pyramid and srf_pack_weights_tc_split() output */
 };
 
 enum srf_dataset { SRF_KITTI = 0, SRF_BUNDLEFUSION = 1 };
@@ -65,7 +69,8 @@ typedef struct srf_mlp_weights {
   const float* fc1_b[SRF_NUM_BLOCKS];
   const float* lin_out_w;                  /* lin_out.weight  (d_out, 512) */
   const float* lin_out_b;
-  const void* tc_packed;                   /* srf_pack_weights_tc() output, or NULL if only fp32 mode is used */
+  const void* tc_packed;                   /* srf_pack_weights_tc() output, or NULL if SRF_PREC_FP16_TC is not used */
+  const void* tc_split_packed;             /* srf_pack_weights_tc_split() output, or NULL if SRF_PREC_FP32_TC is not used */
 } srf_mlp_weights;
 
 /* Feature pyramid of ONE input image, repacked channels-last ([H][W][C] fp32) by srf_pack_pyramid().
@@ -147,6 +152,10 @@ int srf_pack_pyramid(const float* const* chw_dev, const int* C, const int* H, co
 size_t srf_tc_weights_bytes(int d_out, int d_latent);
 /* fp32 nn.Linear tensors -> fp16 K-major, 128B-swizzled shared-memory stage images in MMA consumption order. */
 int srf_pack_weights_tc(const srf_mlp_weights* w, void* dst_dev, size_t dst_bytes, void* stream);
+/* The same stage images for SRF_PREC_FP32_TC: every weight is scaled by a power of two 2^s (max|w| 2^s in
+ * [2^13, 2^14), exact, undone in the epilogues) and stored as two fp16 images, hi = rn(w 2^s) and lo = rn(w 2^s - hi). */
+size_t srf_tc_split_weights_bytes(int d_out, int d_latent);
+int srf_pack_weights_tc_split(const srf_mlp_weights* w, void* dst_dev, size_t dst_bytes, void* stream);
 
 /* --- the hot path ----------------------------------------------------------------------------------------- */
 size_t srf_render_workspace_bytes(const srf_config* cfg, int n_rays);
@@ -248,7 +257,9 @@ int srf_debug_gemm(const float* A, int lda, const float* B, int ldb, float* C, i
 /* Diagnostic (not part of the reference-facing surface): run the tensor-core point MLP of srf_predict but stop each
  * 128-point tile after layer `layer` of the tile program (mlp_tc.cu: 1 lin_in+lin_z0, 2 fc0_0, 4 fc1_0+lin_z1,
  * 5 fc0_1, 7 fc1_1+lin_z2, 8 fc0_2, 9 fc1_2, 10 lin_out) and write the raw fp32 accumulator rows to
- * acc_out_dev (ceil(n/128)*128, 512). */
+ * acc_out_dev (ceil(n/128)*128, 512).  With cfg->precision == SRF_PREC_FP32_TC a tile holds 64 points: rows
+ * 128t..128t+63 are the high-part products of points 64t..64t+63, rows 128t+64..128t+127 their low-part products,
+ * both in units of the weight scale 2^s (acc_out_dev has ceil(n/64)*128 rows). */
 int srf_debug_tc_layer(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w,
                        const float* cam_pts_dev, const float* viewdir_dev, int n_cols, int n_per, int layer,
                        float* acc_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);

@@ -9,11 +9,13 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libscenerf_b200.so")
 
+ABI_VERSION = 2
 NUM_SCALES = 5
 NUM_BLOCKS = 3
 
 PREC_FP32 = 0
 PREC_FP16_TC = 1
+PREC_FP32_TC = 2
 FLAG_SKIP_ZERO_CHUNKS = 1
 FLAG_HIDDEN_FP16 = 2
 FLAG_SAVE_ACTIVATIONS = 4
@@ -32,7 +34,7 @@ class MlpWeights(C.Structure):
                 ("fc0_w", C.c_void_p * NUM_BLOCKS), ("fc0_b", C.c_void_p * NUM_BLOCKS),
                 ("fc1_w", C.c_void_p * NUM_BLOCKS), ("fc1_b", C.c_void_p * NUM_BLOCKS),
                 ("lin_out_w", C.c_void_p), ("lin_out_b", C.c_void_p),
-                ("tc_packed", C.c_void_p)]
+                ("tc_packed", C.c_void_p), ("tc_split_packed", C.c_void_p)]
 
 
 class Pyramid(C.Structure):
@@ -72,6 +74,8 @@ SYMBOLS = {
                                    C.c_int, C.c_void_p, C.c_size_t, C.POINTER(Pyramid), C.c_void_p]),
     "srf_tc_weights_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "srf_pack_weights_tc": (C.c_int, [C.POINTER(MlpWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "srf_tc_split_weights_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "srf_pack_weights_tc_split": (C.c_int, [C.POINTER(MlpWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
     "srf_render_workspace_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int]),
     "srf_render_rays": (C.c_int, [C.POINTER(Config), C.POINTER(Pyramid), C.POINTER(MlpWeights), C.POINTER(MlpWeights),
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Outputs), C.c_void_p,
@@ -119,13 +123,20 @@ def load(build_if_missing: bool = True):
             raise RuntimeError("libscenerf_b200.so is missing: run `python -m scenerf_b200.build`")
         from . import build as _build
         _build.build()
+    elif build_if_missing:
+        # an edited csrc/*.cu must never run as the old binary: rebuild when a source is newer than the library
+        # (skipped silently where nvcc does not exist, e.g. a deployment box that only ships the .so)
+        from . import build as _build
+        if _build._stale() and _build.have_nvcc():
+            _build.build()
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.srf_abi_version() != 1:
-        raise RuntimeError("libscenerf_b200.so ABI version %d != 1" % lib.srf_abi_version())
+    if lib.srf_abi_version() != ABI_VERSION:
+        raise RuntimeError("libscenerf_b200.so ABI version %d != %d (stale build? run python -m scenerf_b200.build --force)"
+                           % (lib.srf_abi_version(), ABI_VERSION))
     for which, st in enumerate((Config, Pyramid, MlpWeights, Outputs)):
         if lib.srf_sizeof(which) != C.sizeof(st):
             raise RuntimeError("struct %s: binding %d bytes, library %d" % (st.__name__, C.sizeof(st), lib.srf_sizeof(which)))

@@ -26,6 +26,12 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def have_nvcc() -> bool:
+    import shutil
+    return any(c and (os.path.exists(c) if os.path.isabs(c) else shutil.which(c)) for c in
+               (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"))
+
+
 def _stale():
     if not os.path.exists(LIB_PATH):
         return True

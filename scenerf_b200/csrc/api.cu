@@ -52,11 +52,11 @@ int validate(const srf_config* cfg, const srf_pyramid* pyr) {
   if (S > 256) return fail(SRF_E_INVALID, "samples per ray S=%d exceeds 256", S);
   if (cfg->sphere_W < 2 || cfg->sphere_H < 2 || cfg->sphere_W > 16384 || cfg->sphere_H > 16384)
     return fail(SRF_E_INVALID, "sphere grid %dx%d outside [2,16384]", cfg->sphere_W, cfg->sphere_H);
-  if (cfg->precision != SRF_PREC_FP32 && cfg->precision != SRF_PREC_FP16_TC)
+  if (cfg->precision != SRF_PREC_FP32 && cfg->precision != SRF_PREC_FP16_TC && cfg->precision != SRF_PREC_FP32_TC)
     return fail(SRF_E_INVALID, "unknown precision %d", cfg->precision);
   if (pyr) {
-    if (cfg->precision == SRF_PREC_FP32 && pyr->format != SRF_PYR_FP32)
-      return fail(SRF_E_INVALID, "precision=FP32 needs a pyramid packed as SRF_PYR_FP32");
+    if (cfg->precision != SRF_PREC_FP16_TC && pyr->format != SRF_PYR_FP32)
+      return fail(SRF_E_INVALID, "precision=FP32 / FP32_TC needs a pyramid packed as SRF_PYR_FP32");
     for (int s = 0; s < SRF_NUM_SCALES; ++s) {
       if (!pyr->hwc[s] || pyr->C[s] < 1 || pyr->H[s] < 1 || pyr->W[s] < 1)
         return fail(SRF_E_INVALID, "pyramid scale %d is empty", s);
@@ -73,6 +73,8 @@ int validate_weights(const srf_mlp_weights* w, int d_out, int d_latent, int prec
     return fail(SRF_E_INVALID, "ResnetFC d_latent=%d but the pyramid has %d channels", w->d_latent, d_latent);
   if (precision == SRF_PREC_FP16_TC && !w->tc_packed)
     return fail(SRF_E_INVALID, "precision=FP16_TC needs srf_pack_weights_tc() output in tc_packed");
+  if (precision == SRF_PREC_FP32_TC && !w->tc_split_packed)
+    return fail(SRF_E_INVALID, "precision=FP32_TC needs srf_pack_weights_tc_split() output in tc_split_packed");
   if (precision == SRF_PREC_FP32) {
     bool ok = w->lin_in_w && w->lin_in_b && w->lin_out_w && w->lin_out_b;
     for (int b = 0; b < SRF_NUM_BLOCKS; ++b)
@@ -158,7 +160,9 @@ int run_mlp(const srf::DevParams& p, int precision, int flags, const srf_mlp_wei
   if (precision == SRF_PREC_FP32 && saved)
     l = srf::run_point_mlp_forward_save(p, w, pts, viewdir, n, n_per, raw, dbg, saved, (flags & SRF_FLAG_TF32_MATMUL) ? 1 : 0, ws, ws_bytes, st);
   else if (precision == SRF_PREC_FP32) l = srf::run_point_mlp_simt(p, w, pts, viewdir, n, n_per, raw, dbg, ws, ws_bytes, st);
-  else l = srf::run_point_mlp_tc(p, w, pts, viewdir, n, n_per, raw, dbg, flags, ws, ws_bytes, st);
+  else
+    l = srf::run_point_mlp_tc(p, w, pts, viewdir, n, n_per, raw, dbg,
+                              precision == SRF_PREC_FP32_TC ? (flags | srf::kTcFlagSplit) : (flags & ~srf::kTcFlagSplit), ws, ws_bytes, st);
   if (l < 0) return fail(SRF_E_WORKSPACE, "point-MLP workspace too small (%zu bytes)", ws_bytes);
   prof_record(2 * pass + 1, st);
   g_launches += l;
@@ -263,16 +267,27 @@ int srf_pack_pyramid(const float* const* chw_dev, const int* C, const int* H, co
   return check_cuda("srf_pack_pyramid");
 }
 
-size_t srf_tc_weights_bytes(int d_out, int d_latent) { return srf::tc_weights_bytes(d_out, d_latent); }
+size_t srf_tc_weights_bytes(int d_out, int d_latent) { return srf::tc_weights_bytes(d_out, d_latent, 0); }
+size_t srf_tc_split_weights_bytes(int d_out, int d_latent) { return srf::tc_weights_bytes(d_out, d_latent, 1); }
+
+static int pack_tc_common(const srf_mlp_weights* w, void* dst_dev, size_t dst_bytes, int split, void* stream, const char* who) {
+  if (!w || !dst_dev) return fail(SRF_E_INVALID, "%s: NULL argument", who);
+  bool ok = w->lin_in_w && w->lin_in_b && w->lin_out_w && w->lin_out_b;
+  for (int b = 0; b < SRF_NUM_BLOCKS; ++b)
+    ok = ok && w->lin_z_w[b] && w->lin_z_b[b] && w->fc0_w[b] && w->fc0_b[b] && w->fc1_w[b] && w->fc1_b[b];
+  if (!ok) return fail(SRF_E_INVALID, "%s: a ResnetFC tensor pointer is NULL", who);
+  const size_t need = srf::tc_weights_bytes(w->d_out, w->d_latent, split);
+  if (dst_bytes < need) return fail(SRF_E_WORKSPACE, "%s: dst has %zu bytes, need %zu", who, dst_bytes, need);
+  const int rc = srf::pack_weights_tc(*w, dst_dev, dst_bytes, split, (cudaStream_t)stream);
+  if (rc) return fail(SRF_E_INVALID, "%s: unsupported shape (d_out=%d d_latent=%d)", who, w->d_out, w->d_latent);
+  return check_cuda(who);
+}
+int srf_pack_weights_tc_split(const srf_mlp_weights* w, void* dst_dev, size_t dst_bytes, void* stream) {
+  return pack_tc_common(w, dst_dev, dst_bytes, 1, stream, "srf_pack_weights_tc_split");
+}
 
 int srf_pack_weights_tc(const srf_mlp_weights* w, void* dst_dev, size_t dst_bytes, void* stream) {
-  if (!w || !dst_dev) return fail(SRF_E_INVALID, "srf_pack_weights_tc: NULL argument");
-  if (dst_bytes < srf::tc_weights_bytes(w->d_out, w->d_latent))
-    return fail(SRF_E_WORKSPACE, "srf_pack_weights_tc: dst has %zu bytes, need %zu", dst_bytes,
-                srf::tc_weights_bytes(w->d_out, w->d_latent));
-  const int rc = srf::pack_weights_tc(*w, dst_dev, dst_bytes, (cudaStream_t)stream);
-  if (rc) return fail(SRF_E_INVALID, "srf_pack_weights_tc: unsupported shape (d_out=%d d_latent=%d)", w->d_out, w->d_latent);
-  return check_cuda("srf_pack_weights_tc");
+  return pack_tc_common(w, dst_dev, dst_bytes, 0, stream, "srf_pack_weights_tc");
 }
 
 size_t srf_render_workspace_bytes(const srf_config* cfg, int n_rays) {
@@ -586,11 +601,12 @@ int srf_debug_tc_layer(const srf_config* cfg, const srf_pyramid* pyr, const srf_
   if (!pyr || !w || !cam_pts_dev || !viewdir_dev || !acc_out_dev || n_cols < 1 || n_per < 1)
     return fail(SRF_E_INVALID, "srf_debug_tc_layer: bad argument");
   const int d_latent = pyramid_channels(pyr);
-  if (int rc = validate_weights(w, w->d_out, d_latent, SRF_PREC_FP16_TC)) return rc;
+  const bool split = cfg->precision == SRF_PREC_FP32_TC;
+  if (int rc = validate_weights(w, w->d_out, d_latent, split ? SRF_PREC_FP32_TC : SRF_PREC_FP16_TC)) return rc;
   const srf::DevParams p = make_params(cfg, pyr);
   const int l = srf::run_point_mlp_tc_debug(p, *w, cam_pts_dev, viewdir_dev, n_cols * n_per, n_per, nullptr, nullptr,
-                                            cfg->flags, workspace_dev, workspace_bytes, layer, acc_out_dev,
-                                            (cudaStream_t)stream);
+                                            split ? (cfg->flags | srf::kTcFlagSplit) : (cfg->flags & ~srf::kTcFlagSplit),
+                                            workspace_dev, workspace_bytes, layer, acc_out_dev, (cudaStream_t)stream);
   if (l == -1) return fail(SRF_E_WORKSPACE, "srf_debug_tc_layer: workspace too small");
   if (l < 0) return fail(SRF_E_INVALID, "srf_debug_tc_layer: layer %d has no accumulator-complete point", layer);
   g_launches += l;

@@ -87,8 +87,10 @@ void launch_ray_backward(const DevParams& p, int R, const float* raw, const floa
                          float* graw_main, float* graw_gauss, cudaStream_t st);
 
 // mlp_tc.cu : tcgen05 tensor-core point MLP.
-size_t tc_weights_bytes(int d_out, int d_latent);
-int pack_weights_tc(const srf_mlp_weights& w, void* dst, size_t bytes, cudaStream_t st);
+//   split != 0: the fp32-grade layout (hi + lo fp16 images of W 2^s, see mlp_tc.cu) read through w.tc_split_packed
+size_t tc_weights_bytes(int d_out, int d_latent, int split);
+int pack_weights_tc(const srf_mlp_weights& w, void* dst, size_t bytes, int split, cudaStream_t st);
+constexpr int kTcFlagSplit = 1 << 30;   // internal bit of the `flags` argument of run_point_mlp_tc*: split (fp32-grade) mode
 size_t tc_workspace_bytes(int d_latent, int n_points);
 int run_point_mlp_tc(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n,
                      int n_per, float* raw_out, int32_t* dbg_sphere, int flags, void* workspace, size_t ws_bytes,

@@ -53,6 +53,8 @@ constexpr int kTmemCols = 512;
 constexpr int kNumBias = 8;                       // c0,c1,c2, b_fc0[0..2], b_fc1_2, b_out(padded)
 constexpr size_t kHeaderBytes = (size_t)kNumBias * kHidden * sizeof(float);   // 16 KB
 constexpr int kNumLayers = 11;
+// split-mode blobs: the power-of-two weight scale 2^s and its inverse live in unused entries of the b_out header row
+constexpr int kScaleSlot = 7 * kHidden + 256, kInvScaleSlot = 7 * kHidden + 257;
 
 // dynamic shared memory carve-up
 constexpr int kSmemA = 0;
@@ -86,6 +88,7 @@ struct KernelArgs {
   int32_t* dbg_sphere;     // (n,2) or null
   int skip_zero;           // SRF_FLAG_SKIP_ZERO_CHUNKS
   int hidden_fp16;         // SRF_FLAG_HIDDEN_FP16: the hidden state travels between blocks as fp16 (scratch bytes halved)
+  int split;               // fp32-grade mode: 64 points per tile, A rows 0-63 = fp16 hi parts, rows 64-127 = lo parts; hi+lo weight images
   int use_tmap;            // CTA pairs: weight images by cp.async.bulk.tensor.cta_group::2 that signals the LEADER's barrier
   int debug_layer;         // -1, or: stop every tile after this layer's ACC is complete and dump it
   float* debug_acc;        // (n_tiles*128, 512)
@@ -289,6 +292,20 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// split mode: (a, b) -> packed fp16 high parts rn(x) and packed low parts rn(x - rn(x)); hi + lo carries 22 mantissa
+// bits (the low part goes subnormal below |x| ~ 2^-3, absolute error <= 2^-25 there)
+__device__ __forceinline__ void split_half2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): start address >> 4 in
 // bits [0,14), leading byte offset (unused for swizzled K-major, =1) in [16,30), stride byte offset (1024 B between
@@ -387,16 +404,17 @@ __device__ __forceinline__ void walk_tile(int kz, uint64_t mask, int last_layer,
 }
 
 // byte offset of the first image of chunk k of layer l inside the image region of the blob
-__device__ __forceinline__ size_t chunk_image_offset(int l, int k, int kz) {
+//   parts = 1 (fp16 images) or 2 (split mode: every image is followed by the image of the fp16 low parts)
+__device__ __forceinline__ size_t chunk_image_offset(int l, int k, int kz, int parts) {
   size_t off = 0;
   for (int i = 0; i < l; ++i) off += (size_t)layer_chunks(i, kz) * (kLayers[i].is_out ? kOutImgBytes : kQuarters * kBSlotBytes);
-  return off + (size_t)k * (kLayers[l].is_out ? kOutImgBytes : kQuarters * kBSlotBytes);
+  return (off + (size_t)k * (kLayers[l].is_out ? kOutImgBytes : kQuarters * kBSlotBytes)) * (size_t)parts;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int CG, bool PROF, bool H16>
+template <int CG, bool PROF, bool H16, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__ KernelArgs a,
                     const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_out) {
@@ -448,6 +466,13 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
   const unsigned char* images = a.wblob + kHeaderBytes;
   constexpr int kMmaN = kBRows * CG;                    // N of one MMA (128 rows from each CTA of the group)
   constexpr int kHalves = kQuarters / CG;               // accumulator column groups of kMmaN: 2 halves (pairs) or 4 quarters
+  // Split (fp32-grade) mode: every fp32 operand x is carried as fp16 hi = rn(x) and lo = rn(x - hi).  The A tile
+  // stacks the two parts of 64 points as ROWS (rows 0-63 hi, rows 64-127 lo -- MMA rows are independent), every
+  // weight image is followed by the image of its low parts and both are accumulated into the same TMEM columns:
+  //   D[r]    = x_hi (W_hi + W_lo)^T ,  D[r+64] = x_lo (W_hi + W_lo)^T ,  result[r] = D[r] + D[r+64]   (epilogue)
+  // i.e. all four partial products with fp32 accumulation, 2 MMAs per 64 points instead of 1 per 128.
+  constexpr int kParts = SPLIT ? 2 : 1;                 // weight images per (chunk, quarter): hi (+ lo)
+  constexpr int kPts = SPLIT ? kTileM / 2 : kTileM;     // points per tile
 
   // ---- visitor pieces shared by producer and relay: which weight images does an op need from THIS CTA? ----------
   //   OP_KOUTER: all column groups of chunk k  -> kHalves images (quarter i*CG + crank)
@@ -474,21 +499,34 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           tma_load_2d_pair(smem_base + kSmemB + rb.slot * kBSlotBytes, tm, 0, row, map_to_cta(bfull(rb.slot), 0), policy);
           rb.advance<kBSlots>();
         }
+        // image (quarter q, part) of a chunk sits at index q * kParts + part (hi then lo in split mode)
+        __device__ __forceinline__ void quarter_t(int row0, int q) {
+          for (int part = 0; part < kParts; ++part) load_t(tmm, row0 + (q * kParts + part) * kBRows, kBSlotBytes);
+        }
+        __device__ __forceinline__ void quarter(const unsigned char* base, int q) {
+          for (int part = 0; part < kParts; ++part) load(base + (size_t)(q * kParts + part) * kBSlotBytes, kBSlotBytes);
+        }
         __device__ __forceinline__ void op(int kind, int l, int k, int h, int) {
           if (CG == 2 && use_tmap) {
-            if (kind == OP_OUT) { load_t(tmo, k * kOutN + (int)crank * (kOutN / 2), kOutImgBytes / 2); return; }
-            const int row0 = (int)(chunk_image_offset(l, k, kz) / 128);
-            if (kind == OP_KOUTER) { for (int i = 0; i < kHalves; ++i) load_t(tmm, row0 + (i * 2 + (int)crank) * kBRows, kBSlotBytes); }
-            else load_t(tmm, row0 + (2 * h + (int)crank) * kBRows, kBSlotBytes);
+            if (kind == OP_OUT) {
+              for (int part = 0; part < kParts; ++part) load_t(tmo, (k * kParts + part) * kOutN + (int)crank * (kOutN / 2), kOutImgBytes / 2);
+              return;
+            }
+            const int row0 = (int)(chunk_image_offset(l, k, kz, kParts) / 128);
+            if (kind == OP_KOUTER) { for (int i = 0; i < kHalves; ++i) quarter_t(row0, i * 2 + (int)crank); }
+            else quarter_t(row0, 2 * h + (int)crank);
             return;
           }
-          const unsigned char* base = images + chunk_image_offset(l, k, kz);
-          if (kind == OP_OUT) { load(base + (size_t)crank * (kOutImgBytes / CG), kOutImgBytes / CG); return; }
+          const unsigned char* base = images + chunk_image_offset(l, k, kz, kParts);
+          if (kind == OP_OUT) {
+            for (int part = 0; part < kParts; ++part) load(base + (size_t)part * kOutImgBytes + (size_t)crank * (kOutImgBytes / CG), kOutImgBytes / CG);
+            return;
+          }
           if (kind == OP_KOUTER) {
-            for (int i = 0; i < kHalves; ++i) load(base + (size_t)(i * CG + crank) * kBSlotBytes, kBSlotBytes);
+            for (int i = 0; i < kHalves; ++i) quarter(base, i * CG + (int)crank);
           } else {
-            if (CG == 2) load(base + (size_t)(2 * h + crank) * kBSlotBytes, kBSlotBytes);
-            else { load(base + (size_t)(2 * h) * kBSlotBytes, kBSlotBytes); load(base + (size_t)(2 * h + 1) * kBSlotBytes, kBSlotBytes); }
+            if (CG == 2) quarter(base, 2 * h + (int)crank);
+            else { quarter(base, 2 * h); quarter(base, 2 * h + 1); }
           }
         }
         __device__ __forceinline__ void ev(int) {}
@@ -523,6 +561,25 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         }
         // weight image(s) of one accumulator column group: wait, 4 MMAs per image pair, release
         __device__ __forceinline__ void mma_group(uint64_t adesc, int n_img, uint32_t dcol, uint32_t idesc, bool fresh) {
+          if constexpr (SPLIT) {
+            // hi image then lo image of every column group, slot by slot (the ring is consumed in order)
+            for (int i = 0; i < n_img; ++i)
+              for (int part = 0; part < 2; ++part) {
+                const long long t0 = (PROF && prof_on) ? clock64() : 0;
+                mbar_wait_cluster(bfull(rb.slot), rb.phase, err);
+                if (PROF && prof_on) wb += clock64() - t0;
+                const int slot = rb.slot;
+                rb.advance<kBSlots>();
+                tc_fence_after();
+                const uint64_t bdesc = make_desc_sw128(smem_base + kSmemB + slot * kBSlotBytes);
+#pragma unroll
+                for (int k = 0; k < kChunkK / 16; ++k)
+                  umma_f16<CG>(tmem_base + dcol + (uint32_t)(i * kMmaN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                               (fresh && k == 0 && part == 0) ? 0u : 1u);
+                umma_commit<CG>(bempty(slot));
+              }
+            return;
+          }
           int bs[2];
           for (int i = 0; i < n_img; ++i) {
             const long long t0 = (PROF && prof_on) ? clock64() : 0;
@@ -601,7 +658,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           rb.advance<kBSlots>();
         }
         __device__ __forceinline__ void op(int kind, int, int, int, int) {
-          if (kind == OP_KOUTER) { for (int i = 0; i < kHalves; ++i) fwd(); } else fwd();
+          const int n = (kind == OP_KOUTER ? kHalves : 1) * kParts;
+          for (int i = 0; i < n; ++i) fwd();
         }
         __device__ __forceinline__ void ev(int) {}
       } rel{bar0, a.error_flag, Ring()};
@@ -657,7 +715,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
 
     for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
       const int tile = grp_i * CG + (int)crank;
-      const int row0 = tile * kTileM;
+      const int row0 = tile * kPts;
       fa = 0;
       // ---------------- front-end: geometry of a tile's 128 points (threads 0..127, one point each) -----------
       // With zero-chunk skipping in a CTA pair, threads 128..255 (idle here otherwise) run the same geometry for the
@@ -665,11 +723,12 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       // The geometry of tile it+1 is computed while tile `it` waits for its last fc_1 (double-buffered sph / mask).
       auto geometry = [&](int grp, int it_) {
         uint32_t my_scales = 0;
-        const bool own = wt < kTileM;
+        const bool own = wt < kPts;
+        const bool for_peer = wt >= kTileM && wt < kTileM + kPts;
         const int trow = own ? wt : wt - kTileM;
         const int ttile = grp * CG + (own ? (int)crank : (1 - (int)crank));
-        if (own || (CG == 2 && a.skip_zero)) {
-          const int gi = ttile * kTileM + trow;
+        if (own || (for_peer && CG == 2 && a.skip_zero)) {
+          const int gi = ttile * kPts + trow;
           int sx = kSphereInvalid, sy = kSphereInvalid;
           if (gi < a.n) {
             point_to_sphere(p, a.pts[(size_t)gi * 3 + 0], a.pts[(size_t)gi * 3 + 1], a.pts[(size_t)gi * 3 + 2], sx, sy);
@@ -714,7 +773,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           // L2 prefetches of the row's gather taps
           const bool first = wt < kTileM;
           const int xrow = first ? wt : wt - kTileM;
-          const int gi = row0 + xrow;
+          const bool xlive = xrow < kPts;           // split mode: rows 64..127 are the low parts, written by the thread of row-64
+          const int gi = xlive ? row0 + xrow : a.n;
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
           float qx = 0.f, qy = 0.f, qz = 0.f;
           if (gi < a.n) { qx = a.pts[(size_t)gi * 3 + 0]; qy = a.pts[(size_t)gi * 3 + 1]; qz = a.pts[(size_t)gi * 3 + 2]; }
@@ -733,12 +793,27 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             if (idx < kDX) return vd[idx - 39];
             return 0.0f;
           };
-          if (first) {
+          // one 16-byte granule (8 values) of row xrow; split mode: high parts to xrow, low parts to xrow + 64
+          auto put_granule = [&](int g, const float* vd) {
+            float v[8];
 #pragma unroll
-            for (int g = 0; g < 3; ++g)
-              sts128(slot_addr + sw128_offset(xrow, g), pack_half2(xval(8 * g + 0, nullptr), xval(8 * g + 1, nullptr)),
-                     pack_half2(xval(8 * g + 2, nullptr), xval(8 * g + 3, nullptr)), pack_half2(xval(8 * g + 4, nullptr), xval(8 * g + 5, nullptr)),
-                     pack_half2(xval(8 * g + 6, nullptr), xval(8 * g + 7, nullptr)));
+            for (int j = 0; j < 8; ++j) v[j] = xval(8 * g + j, vd);
+            if constexpr (SPLIT) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) split_half2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+              sts128(slot_addr + sw128_offset(xrow, g), hi[0], hi[1], hi[2], hi[3]);
+              sts128(slot_addr + sw128_offset(xrow + kPts, g), lo[0], lo[1], lo[2], lo[3]);
+            } else {
+              sts128(slot_addr + sw128_offset(xrow, g), pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
+                     pack_half2(v[6], v[7]));
+            }
+          };
+          if (!xlive) {
+            // nothing: this row of the tile belongs to the thread of point row - 64
+          } else if (first) {
+#pragma unroll
+            for (int g = 0; g < 3; ++g) put_granule(g, nullptr);
           } else {
             float vd[3] = {0.f, 0.f, 0.f};
             if (gi < a.n) {
@@ -746,10 +821,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
               vd[0] = vp[0]; vd[1] = vp[1]; vd[2] = vp[2];
             }
 #pragma unroll
-            for (int g = 3; g < 8; ++g)
-              sts128(slot_addr + sw128_offset(xrow, g), pack_half2(xval(8 * g + 0, vd), xval(8 * g + 1, vd)),
-                     pack_half2(xval(8 * g + 2, vd), xval(8 * g + 3, vd)), pack_half2(xval(8 * g + 4, vd), xval(8 * g + 5, vd)),
-                     pack_half2(xval(8 * g + 6, vd), xval(8 * g + 7, vd)));
+            for (int g = 3; g < 8; ++g) put_granule(g, vd);
             // warm L2 with the taps this row will gather from the (usually in-bounds) fine scales: the gather runs
             // thousands of cycles later and then sees L2 instead of HBM latency
             const short2 sp16 = sph_cur[xrow];
@@ -781,6 +853,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       // The gathered chunks of the fine scales (chunks 0..kZCache-1: the ones that normally carry data) are identical
       // for lin_z0/1/2: pass 0 also writes their fp16 tile images to an L2-resident per-CTA cache, passes 1 and 2
       // bring them back with one cp.async.bulk each (all in flight together) instead of gathering again.
+      constexpr int kItems = kPts / 32;           // rows per thread and chunk: (wt/8) + 32*i
       auto gather_pass = [&](int pass) {
         const int g = wt & 7;
         int first_c = 0;
@@ -821,6 +894,22 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             sts128(slot_addr_ + off, w0, w1, w2, w3);
             if (zc) *reinterpret_cast<uint4*>(zc + off) = make_uint4(w0, w1, w2, w3);
           };
+          // 8 gathered channels of one point: fp16 operands (split mode: high parts to `row`, low parts to row + 64)
+          auto emit_vals = [&](int row, const float (&v)[8], uint32_t slot_addr_) {
+            if constexpr (SPLIT) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) split_half2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+              emit(row, hi[0], hi[1], hi[2], hi[3], slot_addr_);
+              emit(row + kPts, lo[0], lo[1], lo[2], lo[3], slot_addr_);
+            } else {
+              emit(row, pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]), slot_addr_);
+            }
+          };
+          auto emit_zero = [&](int row, uint32_t slot_addr_) {
+            emit(row, 0u, 0u, 0u, 0u, slot_addr_);
+            if constexpr (SPLIT) emit(row + kPts, 0u, 0u, 0u, 0u, slot_addr_);
+          };
           int s = -1;
 #pragma unroll
           for (int i = 0; i < kScales; ++i)
@@ -828,7 +917,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           if (s >= 0 && s != cur_scale) {
             dxo = p.C[s]; dyo = p.W[s] * p.C[s];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kItems; ++i) {
               const short2 sp16 = sph_cur[(wt >> 3) + 32 * i];
               const int2 sp = make_int2(sp16.x, sp16.y);
               const Taps tp = scale_taps(p, s, sp.x, sp.y);
@@ -858,17 +947,21 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           const char* fbytes = (s >= 0) ? reinterpret_cast<const char*>(p.feat[s]) : nullptr;
           const int ch_in = (s >= 0) ? ch - p.ch_off[s] : 0;
           const bool f16 = p.feat_fp16 != 0;
-          const uint32_t any_live = (s >= 0) ? (t_ok[0] | t_ok[1] | t_ok[2] | t_ok[3]) : 0u;
+          uint32_t any_live = 0u;
+          if (s >= 0) {
+#pragma unroll
+            for (int u = 0; u < kItems; ++u) any_live |= t_ok[u];
+          }
           if (!any_live) {
             // nothing to gather for this thread's rows (the normal case for the coarse scales): zeros
 #pragma unroll
-            for (int u = 0; u < 4; ++u) emit((wt >> 3) + 32 * u, 0u, 0u, 0u, 0u, slot_addr);
+            for (int u = 0; u < kItems; ++u) emit_zero((wt >> 3) + 32 * u, slot_addr);
           } else if (f16) {
             // fp16 pyramid: a tap of 8 channels is ONE 128-bit load -> all 16 taps of the thread's 4 items are
             // requested together (one memory round trip per chunk)
-            uint4 raw[4][4];
+            uint4 raw[kItems][4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kItems; ++u) {
               const uint32_t ok = (s >= 0) ? t_ok[u] : 0u;
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
@@ -881,9 +974,9 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
               }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kItems; ++u) {
               const int row = (wt >> 3) + 32 * u;
-              if (!((s >= 0) && t_ok[u])) { emit(row, 0u, 0u, 0u, 0u, slot_addr); continue; }
+              if (!((s >= 0) && t_ok[u])) { emit_zero(row, slot_addr); continue; }
               const float w = t_w[u], n = t_n[u];
               const float e = fsub(1.0f, w), so = fsub(1.0f, n);
               const float tw4[4] = {fmul(so, e), fmul(so, w), fmul(n, e), fmul(n, w)};     // nw, ne, sw, se
@@ -899,17 +992,16 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
                   else { acc[2 * q] = fadd(acc[2 * q], fmul(f.x, wt_)); acc[2 * q + 1] = fadd(acc[2 * q + 1], fmul(f.y, wt_)); }
                 }
               }
-              emit(row, pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
-                     pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]), slot_addr);
+              emit_vals(row, acc, slot_addr);
             }
           } else {
           // two items at a time: their (up to) 16 tap loads are requested before the first one is consumed
 #pragma unroll
-          for (int ib = 0; ib < 4; ib += 2) {
+          for (int ib = 0; ib < kItems; ib += 2) {
             const bool live0 = (s >= 0) && t_ok[ib], live1 = (s >= 0) && t_ok[ib + 1];
             if (!live0 && !live1) {                               // the common case for the coarse scales
-              emit((wt >> 3) + 32 * ib, 0u, 0u, 0u, 0u, slot_addr);
-              emit((wt >> 3) + 32 * (ib + 1), 0u, 0u, 0u, 0u, slot_addr);
+              emit_zero((wt >> 3) + 32 * ib, slot_addr);
+              emit_zero((wt >> 3) + 32 * (ib + 1), slot_addr);
               continue;
             }
             float4 v[2][4][2];
@@ -952,8 +1044,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
                   acc[6] = fadd(acc[6], fmul(a1.z, wt_)); acc[7] = fadd(acc[7], fmul(a1.w, wt_));
                 }
               }
-              emit(row, pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
-                     pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7]), slot_addr);
+              emit_vals(row, acc, slot_addr);
             }
           }
           }
@@ -1065,6 +1156,90 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         lap(write_h ? 3 : (use_h ? 6 : 5));
       };
 
+      // ---------------- split mode: the same epilogue for a 64-point tile --------------------------------------------
+      //   TMEM lane r (warps of lane quarters 0,1: "hi warps") holds x_hi W^T, lane r + 64 (quarters 2,3: "lo warps")
+      //   x_lo W^T of the same point.  A warp can only read its own lane quarter, so the lo warp hands its 16 values
+      //   per group to its partner (same sub, quarter - 2) through shared memory -- through exactly the 64 bytes of the
+      //   next layer's A tile that the partner lane is about to overwrite with the finished operands (rows r and r+64,
+      //   two granules), so no staging buffer is needed; one 64-thread named barrier per group orders the hand-over.
+      //   The hi warp does all the arithmetic: (D_hi + D_lo) * 2^-s + bias (+ h), ReLU, hi/lo split, A-tile stores.
+      auto epilogue_half_split = [&](int part, int bias_idx, bool use_h, bool write_h) {
+        lap(1);
+        mbar_wait(half_full(part), half_par[part], a.error_flag);
+        half_par[part] ^= 1;
+        tc_fence_after();
+        lap(2);
+        const bool hi_warp = q4 < 2;
+        const int pair_bar = 2 + (q4 & 1) * 2 + sub;            // named barriers 2..5: one per (hi, lo) warp pair
+        const int prow = (q4 & 1) * 32 + lane;                  // point row (0..63) this lane works on
+        const float4* b4 = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden);
+        const float inv_scale = __ldg(bias + kInvScaleSlot);
+        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        const int col0 = part * 256 + sub * 128;
+        uint32_t vn[16];
+        float4 hn[4];
+        auto load_h = [&](float4 (&dst)[4], int c) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = (use_h && hi_warp) ? scratch4[(size_t)((c >> 2) + j) * kTileM + prow] : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        tmem_ld16(trow + (uint32_t)col0, vn);
+        load_h(hn, col0);
+        for (int grp = 0; grp < 8; ++grp) {
+          const int col = col0 + grp * 16;
+          const int slot = col >> 6;
+          if ((grp & 3) == 0) wait_slot_free(slot);
+          const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
+          const int gcol = (col & 63) >> 3;
+          const uint32_t ex[4] = {slot_addr + sw128_offset(prow, gcol), slot_addr + sw128_offset(prow, gcol + 1),
+                                  slot_addr + sw128_offset(prow + kPts, gcol), slot_addr + sw128_offset(prow + kPts, gcol + 1)};
+          tmem_ld_wait();
+          uint32_t v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = vn[j];
+          if (grp < 7) tmem_ld16(trow + (uint32_t)(col + 16), vn);
+          if (!hi_warp) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sts128(ex[j], v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            named_bar_sync(pair_bar, 64);
+            continue;
+          }
+          float4 bb[4], hh[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { bb[j] = __ldg(b4 + (col >> 2) + j); hh[j] = hn[j]; }
+          if (grp < 7) load_h(hn, col + 16);
+          named_bar_sync(pair_bar, 64);
+          float r[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 pl = lds128(ex[j]);
+            r[4 * j + 0] = (__uint_as_float(v[4 * j + 0]) + __uint_as_float(pl.x)) * inv_scale + bb[j].x + hh[j].x;
+            r[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + __uint_as_float(pl.y)) * inv_scale + bb[j].y + hh[j].y;
+            r[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + __uint_as_float(pl.z)) * inv_scale + bb[j].z + hh[j].z;
+            r[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + __uint_as_float(pl.w)) * inv_scale + bb[j].w + hh[j].w;
+            if (write_h) scratch4[(size_t)((col >> 2) + j) * kTileM + prow] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split_half2(fmaxf(r[2 * j], 0.0f), fmaxf(r[2 * j + 1], 0.0f), hi[j], lo[j]);
+          sts128(ex[0], hi[0], hi[1], hi[2], hi[3]);
+          sts128(ex[1], hi[4], hi[5], hi[6], hi[7]);
+          sts128(ex[2], lo[0], lo[1], lo[2], lo[3]);
+          sts128(ex[3], lo[4], lo[5], lo[6], lo[7]);
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0)
+          for (int s = 4 * part; s < 4 * part + 4; ++s) arrive_a_full(s);
+        fill_par ^= 0xFu << (4 * part);
+        lap(write_h ? 3 : (use_h ? 6 : 5));
+      };
+      auto epilogue = [&](int part, int bias_idx, bool use_h, bool write_h) {
+        if constexpr (SPLIT) epilogue_half_split(part, bias_idx, use_h, write_h);
+        else epilogue_half(part, bias_idx, use_h, write_h);
+      };
+
       auto dump_acc = [&](bool both_halves) {     // debug: raw accumulator of the current layer
         mbar_wait(half_full(0), half_par[0], a.error_flag);
         half_par[0] ^= 1;
@@ -1075,7 +1250,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)col, v);
           tmem_ld_wait();
-          float* dst = a.debug_acc + ((size_t)row0 + erow) * kHidden + col;
+          float* dst = a.debug_acc + ((size_t)tile * kTileM + erow) * kHidden + col;   // split mode: rows 64-127 = low-part products
           if (tile < a.n_tiles) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(v[j]);
@@ -1091,11 +1266,11 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       if (a.debug_layer == 1) { dump_acc(true); continue; }
       bool stop = false;
       for (int b = 0; b < SRF_NUM_BLOCKS; ++b) {
-        epilogue_half(0, b, b > 0, true);                         // E1a -> A chunks 0-3 of fc_0
-        epilogue_half(1, b, b > 0, true);                         // E1b
+        epilogue(0, b, b > 0, true);                              // E1a -> A chunks 0-3 of fc_0
+        epilogue(1, b, b > 0, true);                              // E1b
         if (a.debug_layer == 2 + 3 * b) { dump_acc(true); stop = true; break; }
-        epilogue_half(0, 3 + b, false, false);                    // E2a -> A chunks 0-3 of fc_1 (overlaps fc_0 S4)
-        epilogue_half(1, 3 + b, false, false);                    // E2b (overlaps fc_1 S1)
+        epilogue(0, 3 + b, false, false);                         // E2a -> A chunks 0-3 of fc_1 (overlaps fc_0 S4)
+        epilogue(1, 3 + b, false, false);                         // E2b (overlaps fc_1 S1)
         if (b < SRF_NUM_BLOCKS - 1) {
           gather_pass(b + 1);                                     // lin_z(b+1), consumed between fc_1 S2 and S3
           if (a.debug_layer == 4 + 3 * b) { dump_acc(true); stop = true; break; }
@@ -1106,8 +1281,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         }
       }
       if (stop) continue;
-      epilogue_half(0, 6, true, false);                           // E3a -> A chunks of lin_out
-      epilogue_half(1, 6, true, false);                           // E3b
+      epilogue(0, 6, true, false);                                // E3a -> A chunks of lin_out
+      epilogue(1, 6, true, false);                                // E3b
       if (a.debug_layer == 10) { dump_acc(false); continue; }
       // ---------------- E4: out = ACC[:, :d_out] + b_out ------------------------------------------------------
       lap(1);
@@ -1119,10 +1294,38 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16), v);   // 16 columns
         tmem_ld_wait();
-        const int gi = row0 + erow;
-        if (gi < a.n) {
-          const float* bo = bias + (size_t)7 * kHidden;
-          for (int j = 0; j < a.d_out; ++j) a.raw_out[(size_t)gi * a.d_out + j] = __uint_as_float(v[j]) + __ldg(bo + j);
+        const float* bo = bias + (size_t)7 * kHidden;
+        if constexpr (SPLIT) {
+          // lanes r and r + 64 hold the two halves of the sum: the lo warp passes its 16 values through the (drained)
+          // last A slot; every MMA that read it has completed (EV_OUT is committed after the lin_out MMAs)
+          const int prow = (q4 & 1) * 32 + lane;
+          const uint32_t ex = smem_base + kSmemA + 7 * kASlotBytes + (uint32_t)prow * 64u;
+          if (q4 >= 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sts128(ex + 16 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            named_bar_sync(2 + (q4 & 1) * 2, 64);
+          } else {
+            named_bar_sync(2 + (q4 & 1) * 2, 64);
+            float pl[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 t4 = lds128(ex + 16 * j);
+              pl[4 * j] = __uint_as_float(t4.x); pl[4 * j + 1] = __uint_as_float(t4.y);
+              pl[4 * j + 2] = __uint_as_float(t4.z); pl[4 * j + 3] = __uint_as_float(t4.w);
+            }
+            const float inv_scale = __ldg(bias + kInvScaleSlot);
+            const int gi = row0 + prow;
+            if (gi < a.n) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < a.d_out) a.raw_out[(size_t)gi * a.d_out + j] = (__uint_as_float(v[j]) + pl[j]) * inv_scale + __ldg(bo + j);
+            }
+          }
+        } else {
+          const int gi = row0 + erow;
+          if (gi < a.n) {
+            for (int j = 0; j < a.d_out; ++j) a.raw_out[(size_t)gi * a.d_out + j] = __uint_as_float(v[j]) + __ldg(bo + j);
+          }
         }
       }
       tc_fence_before();
@@ -1153,6 +1356,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
 struct PackArgs {
   srf_mlp_weights w;
   int kz;
+  int parts;               // 1: fp16 images; 2: split mode, image (q, part) at index q*2 + part, part 0 = rn(W 2^s), 1 = rn(W 2^s - hi)
 };
 
 __device__ __forceinline__ const float* layer_weight(const srf_mlp_weights& w, int l, int& K) {
@@ -1172,26 +1376,59 @@ __device__ __forceinline__ const float* layer_weight(const srf_mlp_weights& w, i
   }
 }
 
+// split mode: largest |w| over the 11 weight matrices -> power-of-two scale 2^s with max|w| 2^s in [2^13, 2^14), so
+// that the fp16 low parts of typical weights are normal numbers (unscaled, |w| ~ 0.06 has a subnormal low part).
+// Scaling by a power of two and its inverse in the epilogue are exact.
+__global__ void weight_absmax_kernel(const __grid_constant__ PackArgs pa, unsigned int* __restrict__ max_bits) {
+  float m = 0.0f;
+  for (int l = 0; l < kNumLayers; ++l) {
+    int K;
+    const float* W = layer_weight(pa.w, l, K);
+    const size_t n = (size_t)(l == kNumLayers - 1 ? pa.w.d_out : kHidden) * K;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(W[i]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(max_bits, __float_as_uint(m));       // non-negative floats order like their bits
+}
+__global__ void weight_scale_kernel(const unsigned int* __restrict__ max_bits, float* __restrict__ hdr, int split) {
+  float scale = 1.0f;
+  if (split) {
+    const float m = __uint_as_float(*max_bits);
+    int e = 0;
+    if (m > 0.0f && isfinite(m)) { frexpf(m, &e); e = 14 - e; }        // m < 2^e0  ->  m 2^(14-e0) < 2^14
+    e = max(-40, min(40, e));
+    scale = ldexpf(1.0f, e);
+  }
+  hdr[kScaleSlot] = scale;
+  hdr[kInvScaleSlot] = 1.0f / scale;
+}
+
 // one thread per 16-byte granule of the image region
-__global__ void pack_images_kernel(const __grid_constant__ PackArgs pa, unsigned char* __restrict__ images, size_t n_granules) {
+__global__ void pack_images_kernel(const __grid_constant__ PackArgs pa, const float* __restrict__ hdr, unsigned char* __restrict__ images,
+                                   size_t n_granules) {
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n_granules) return;
   size_t byte = gid * 16;
+  const int parts = pa.parts;
+  const float scale = hdr[kScaleSlot];
   // locate the layer
   int l = 0;
   size_t off = 0;
   for (; l < kNumLayers; ++l) {
-    const size_t sz = (size_t)layer_chunks(l, pa.kz) * (kLayers[l].is_out ? kOutImgBytes : kQuarters * kBSlotBytes);
+    const size_t sz = (size_t)layer_chunks(l, pa.kz) * (kLayers[l].is_out ? kOutImgBytes : kQuarters * kBSlotBytes) * parts;
     if (byte < off + sz) break;
     off += sz;
   }
   const size_t rel = byte - off;
   const bool is_out = kLayers[l].is_out;
-  const size_t chunk_bytes = is_out ? kOutImgBytes : (size_t)kQuarters * kBSlotBytes;
+  const size_t img_bytes = is_out ? kOutImgBytes : kBSlotBytes;
+  const size_t chunk_bytes = (is_out ? 1 : kQuarters) * img_bytes * parts;
   const int c = (int)(rel / chunk_bytes);
   const size_t in_chunk = rel % chunk_bytes;
-  const int q = is_out ? 0 : (int)(in_chunk / kBSlotBytes);
-  const size_t in_img = is_out ? in_chunk : in_chunk % kBSlotBytes;
+  const int img = (int)(in_chunk / img_bytes);          // q * parts + part
+  const int q = img / parts, part = img % parts;
+  const size_t in_img = in_chunk % img_bytes;
   const int row = (int)(in_img / 128);
   const int gpos = (int)((in_img % 128) / 16);
   const int g = gpos ^ (row & 7);                      // logical granule stored at this swizzled position
@@ -1203,8 +1440,9 @@ __global__ void pack_images_kernel(const __grid_constant__ PackArgs pa, unsigned
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = c * kChunkK + g * 8 + j;
-    const float v = (n < n_rows && k < K) ? W[(size_t)n * K + k] : 0.0f;
-    hv[j] = __float2half_rn(v);
+    const float v = ((n < n_rows && k < K) ? W[(size_t)n * K + k] : 0.0f) * scale;
+    const __half hi = __float2half_rn(v);
+    hv[j] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
   }
   *reinterpret_cast<uint4*>(images + byte) = *reinterpret_cast<const uint4*>(hv);
 }
@@ -1224,33 +1462,43 @@ __global__ void pack_header_kernel(const __grid_constant__ PackArgs pa, float* _
   hdr[7 * kHidden + j] = (j < w.d_out) ? w.lin_out_b[j] : 0.0f;
 }
 
-static size_t images_bytes(int kz) {
+static size_t images_bytes(int kz, int parts = 1) {
   size_t b = 0;
   const int chunks[kNumLayers] = {1, kz, 8, 8, kz, 8, 8, kz, 8, 8, 8};
   for (int l = 0; l < kNumLayers; ++l) b += (size_t)chunks[l] * (l == kNumLayers - 1 ? kOutImgBytes : kQuarters * kBSlotBytes);
-  return b;
+  return b * (size_t)parts;
 }
 
 }  // namespace tc
 
 static inline int kz_of(int d_latent) { return (d_latent + tc::kChunkK - 1) / tc::kChunkK; }
 
-size_t tc_weights_bytes(int d_out, int d_latent) {
+size_t tc_weights_bytes(int d_out, int d_latent, int split) {
   (void)d_out;
-  return tc::kHeaderBytes + tc::images_bytes(kz_of(d_latent)) + 256;
+  // + 256: slack; the last 4 bytes of the blob are the absmax scratch word of the split pack
+  return tc::kHeaderBytes + tc::images_bytes(kz_of(d_latent), split ? 2 : 1) + 256;
 }
 
-int pack_weights_tc(const srf_mlp_weights& w, void* dst, size_t bytes, cudaStream_t st) {
+int pack_weights_tc(const srf_mlp_weights& w, void* dst, size_t bytes, int split, cudaStream_t st) {
   const int kz = kz_of(w.d_latent);
   if (kz > 64 || w.d_out < 1 || w.d_out > tc::kOutN || (w.d_latent % 8)) return 1;
-  if (bytes < tc_weights_bytes(w.d_out, w.d_latent)) return 1;
+  const size_t need = tc_weights_bytes(w.d_out, w.d_latent, split);
+  if (bytes < need) return 1;
   tc::PackArgs pa;
   pa.w = w;
   pa.kz = kz;
-  tc::pack_header_kernel<<<(kHidden + 127) / 128, 128, 0, st>>>(pa, reinterpret_cast<float*>(dst));
-  const size_t n_gran = tc::images_bytes(kz) / 16;
+  pa.parts = split ? 2 : 1;
+  float* hdr = reinterpret_cast<float*>(dst);
+  unsigned int* max_bits = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(dst) + need - 4);
+  tc::pack_header_kernel<<<(kHidden + 127) / 128, 128, 0, st>>>(pa, hdr);
+  if (split) {
+    cudaMemsetAsync(max_bits, 0, 4, st);
+    tc::weight_absmax_kernel<<<296, 256, 0, st>>>(pa, max_bits);
+  }
+  tc::weight_scale_kernel<<<1, 1, 0, st>>>(max_bits, hdr, split ? 1 : 0);
+  const size_t n_gran = tc::images_bytes(kz, pa.parts) / 16;
   tc::pack_images_kernel<<<(unsigned)((n_gran + 255) / 256), 256, 0, st>>>(
-      pa, reinterpret_cast<unsigned char*>(dst) + tc::kHeaderBytes, n_gran);
+      pa, hdr, reinterpret_cast<unsigned char*>(dst) + tc::kHeaderBytes, n_gran);
   return 0;
 }
 
@@ -1304,13 +1552,20 @@ static bool tc_use_tmap() {
 }
 
 using TcKernelFn = void (*)(const DevParams, const tc::KernelArgs, const CUtensorMap, const CUtensorMap);
-static TcKernelFn tc_kernel(int cg, bool prof, bool h16) {
-  static const TcKernelFn table[8] = {
-      tc::point_mlp_tc_kernel<1, false, false>, tc::point_mlp_tc_kernel<2, false, false>,
-      tc::point_mlp_tc_kernel<1, true, false>,  tc::point_mlp_tc_kernel<2, true, false>,
-      tc::point_mlp_tc_kernel<1, false, true>,  tc::point_mlp_tc_kernel<2, false, true>,
-      tc::point_mlp_tc_kernel<1, true, true>,   tc::point_mlp_tc_kernel<2, true, true>};
-  return table[(cg == 2 ? 1 : 0) | (prof ? 2 : 0) | (h16 ? 4 : 0)];
+constexpr int kNumTcKernels = 12;
+// index: bit 0 = CTA pairs, bit 1 = profiling counters, then 0 = fp32 hidden state, 4 = fp16 hidden state, 8 = split mode
+static TcKernelFn tc_kernel_at(int i) {
+  static const TcKernelFn table[kNumTcKernels] = {
+      tc::point_mlp_tc_kernel<1, false, false, false>, tc::point_mlp_tc_kernel<2, false, false, false>,
+      tc::point_mlp_tc_kernel<1, true, false, false>,  tc::point_mlp_tc_kernel<2, true, false, false>,
+      tc::point_mlp_tc_kernel<1, false, true, false>,  tc::point_mlp_tc_kernel<2, false, true, false>,
+      tc::point_mlp_tc_kernel<1, true, true, false>,   tc::point_mlp_tc_kernel<2, true, true, false>,
+      tc::point_mlp_tc_kernel<1, false, false, true>,  tc::point_mlp_tc_kernel<2, false, false, true>,
+      tc::point_mlp_tc_kernel<1, true, false, true>,   tc::point_mlp_tc_kernel<2, true, false, true>};
+  return table[i];
+}
+static TcKernelFn tc_kernel(int cg, bool prof, bool h16, bool split) {
+  return tc_kernel_at((cg == 2 ? 1 : 0) | (prof ? 2 : 0) | (split ? 8 : (h16 ? 4 : 0)));
 }
 
 static int tc_cta_group() {
@@ -1336,20 +1591,24 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
     return -2;                         // layers without an ACC-complete signal cannot be dumped
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 8; ++i)
-      cudaFuncSetAttribute(tc_kernel(1 + (i & 1), (i & 2) != 0, (i & 4) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           tc::kSmemTotal + 1024);
+    for (int i = 0; i < kNumTcKernels; ++i)
+      cudaFuncSetAttribute(tc_kernel_at(i), cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTotal + 1024);
     attr_set = true;
   }
+  const bool split = (flags & kTcFlagSplit) != 0;
+  const int parts = split ? 2 : 1;
+  const int tile_pts = split ? tc::kTileM / 2 : tc::kTileM;
   tc::KernelArgs a;
   a.pts = pts; a.viewdir = viewdir; a.n = n; a.n_per = n_per;
-  a.n_tiles = (n + tc::kTileM - 1) / tc::kTileM;
+  a.n_tiles = (n + tile_pts - 1) / tile_pts;
+  a.split = split ? 1 : 0;
   a.kz = kz_of(p.d_latent);
-  a.wblob = reinterpret_cast<const unsigned char*>(w.tc_packed);
+  a.wblob = reinterpret_cast<const unsigned char*>(split ? w.tc_split_packed : w.tc_packed);
+  if (!a.wblob) return -3;
   a.scratch = reinterpret_cast<float*>(workspace);
   a.raw_out = raw_out; a.d_out = w.d_out; a.dbg_sphere = dbg_sphere;
   a.skip_zero = (flags & SRF_FLAG_SKIP_ZERO_CHUNKS) ? 1 : 0;
-  a.hidden_fp16 = (flags & SRF_FLAG_HIDDEN_FP16) ? 1 : 0;
+  a.hidden_fp16 = (!split && (flags & SRF_FLAG_HIDDEN_FP16)) ? 1 : 0;
   a.debug_layer = debug_layer; a.debug_acc = debug_acc;
   a.zcache = reinterpret_cast<unsigned char*>(workspace) + (size_t)256 * tc::kTileM * kHidden * sizeof(float);
   if (const char* e = getenv("SRF_TC_ZCACHE")) { if (atoi(e) == 0) a.zcache = nullptr; }
@@ -1385,7 +1644,7 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
     if (!max_pairs) {
       cfg.gridDim = dim3(num_sms() / 2 * 2);
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, tc_kernel(2, false, false), &cfg) != cudaSuccess || nc < 1) nc = num_sms() / 2;
+      if (cudaOccupancyMaxActiveClusters(&nc, tc_kernel(2, false, false, false), &cfg) != cudaSuccess || nc < 1) nc = num_sms() / 2;
       max_pairs = nc;
     }
     max_ctas = max_pairs * 2;
@@ -1400,14 +1659,14 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
   memset(&tm_out, 0, sizeof(tm_out));
   a.use_tmap = 0;
   if (cg == 2 && tc_use_tmap()) {
-    const size_t img_bytes = tc::images_bytes(a.kz);
+    const size_t img_bytes = tc::images_bytes(a.kz, parts);
     unsigned char* img = const_cast<unsigned char*>(a.wblob) + tc::kHeaderBytes;
-    const size_t out_bytes = (size_t)tc::kHiddenChunks * tc::kOutImgBytes;
+    const size_t out_bytes = (size_t)tc::kHiddenChunks * tc::kOutImgBytes * parts;
     if (encode_image_map(&tm_main, img, (img_bytes - out_bytes) / 128, tc::kBRows) &&
         encode_image_map(&tm_out, img + (img_bytes - out_bytes), out_bytes / 128, tc::kOutN / 2))
       a.use_tmap = 1;
   }
-  cudaLaunchKernelEx(&cfg, tc_kernel(cg, prof_env, a.hidden_fp16 != 0), p, a, tm_main, tm_out);
+  cudaLaunchKernelEx(&cfg, tc_kernel(cg, prof_env, a.hidden_fp16 != 0, split), p, a, tm_main, tm_out);
   if (prof_env) {            // diagnostics only: synchronises and prints mean per-CTA cycle counters
     static unsigned long long host[256 * 16];
     cudaStreamSynchronize(st);
@@ -1419,7 +1678,7 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
             cg, grid, tiles, m[4] / tiles / 1e3, m[0] / tiles / 1e3, m[1] / tiles / 1e3, m[7] / tiles / 1e3, m[2] / tiles / 1e3,
             m[3] / tiles / 1e3, m[5] / tiles / 1e3, m[6] / tiles / 1e3, cg, m[8] * cg / tiles / 1e3, m[9] * cg / tiles / 1e3);
   }
-  return 2;
+  return 1;
 }
 
 int run_point_mlp_tc(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n,

@@ -22,7 +22,7 @@ SCALE_KEYS = ("1_1", "1_2", "1_4", "1_8", "1_16")
 DICT_KEYS = ("depth", "color", "gaussian_means", "gaussian_stds", "weights_at_depth", "closest_pts_to_depths",
              "loss_kl", "alphas", "som_vars", "densities", "weights", "depth_volumes")
 MINIMAL_KEYS = ("depth", "color")
-PRECISIONS = {"fp32": _lib.PREC_FP32, "fp16": _lib.PREC_FP16_TC}
+PRECISIONS = {"fp32": _lib.PREC_FP32, "fp16": _lib.PREC_FP16_TC, "fp32tc": _lib.PREC_FP32_TC}
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -36,7 +36,7 @@ def _stream_ptr(device):
 class _PackedMlp:
     """Keeps the 22 nn.Linear tensors of a ResnetFC alive (fp32, contiguous, on device) + the tensor-core pack."""
 
-    def __init__(self, state: Dict[str, torch.Tensor], d_out: int, device, want_tc: bool):
+    def __init__(self, state: Dict[str, torch.Tensor], d_out: int, device, want_tc: bool, want_split: bool = False):
         lib = _lib.load()
         g = lambda k: state[k].detach().to(device=device, dtype=torch.float32).contiguous()
         self.tensors = {k: g(k) for k in state}
@@ -61,6 +61,12 @@ class _PackedMlp:
             self.packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
             _lib.check(lib.srf_pack_weights_tc(C.byref(w), _ptr(self.packed), nbytes, _stream_ptr(device)))
             w.tc_packed = self.packed.data_ptr()
+        self.packed_split = None
+        if want_split:
+            nbytes = lib.srf_tc_split_weights_bytes(d_out, w.d_latent)
+            self.packed_split = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            _lib.check(lib.srf_pack_weights_tc_split(C.byref(w), _ptr(self.packed_split), nbytes, _stream_ptr(device)))
+            w.tc_split_packed = self.packed_split.data_ptr()
         self.struct = w
 
 
@@ -71,7 +77,9 @@ class B200Renderer:
         n_pts_per_gaussian, std, max_sample_depth, out_img_W, out_img_H, som_sigma, v_angle_min/max,
         h_angle_min/max (SphericalMapping incl. add_fov).
     mlp_state / mlp_gaussian_state: ResnetFC state dicts (resnetfc.py parameter names).
-    precision: "fp16" tensor cores (tcgen05, fp32 accumulate) or "fp32" strict SIMT.
+    precision: "fp32tc" tensor cores at float32-grade accuracy (fp16 hi/lo split operands, fp32 accumulate: the
+         precision-matched mode for the reference's fp32 sgemm), "fp16" tensor cores with fp16 operands (fast mode),
+         or "fp32" strict SIMT FMA.
     rng: "torch" reproduces the reference's two RNG calls (utils.py:84, 208-211) chunk by chunk so that seeded runs
          see identical noise; "philox" draws in-kernel (no noise tensors, fastest).
     """
@@ -93,10 +101,11 @@ class B200Renderer:
         self.skip_zero_chunks = skip_zero_chunks
         self.pyramid_fp16 = pyramid_fp16      # fp16 mode: store the packed pyramid as fp16 (half the gather bytes)
         self.hidden_fp16 = hidden_fp16        # fp16 mode: residual hidden state carried between blocks as fp16
-        want_tc = precision == "fp16"
-        self.mlp = _PackedMlp(mlp_state, 4, self.device, want_tc)
-        self.mlp_gaussian = _PackedMlp(mlp_gaussian_state, 2, self.device, want_tc)
+        want_tc, want_split = precision == "fp16", precision == "fp32tc"
+        self.mlp = _PackedMlp(mlp_state, 4, self.device, want_tc, want_split)
+        self.mlp_gaussian = _PackedMlp(mlp_gaussian_state, 2, self.device, want_tc, want_split)
         self._pyr_key = None
+        self._pyr_held = None
         self._pyr_buf = None
         self._pyr = None
         self._ws = None
@@ -123,8 +132,12 @@ class B200Renderer:
     # ------------------------------------------------------------------------------------------------------------
     def _pack_pyramid(self, x_rgb: Dict[str, torch.Tensor]):
         ts = [x_rgb[k] for k in SCALE_KEYS]
-        key = tuple((t.data_ptr(), tuple(t.shape), t._version) for t in ts)
-        if key == self._pyr_key:
+        # The cached pack is reused only for the very same tensor OBJECTS, unmodified (same storage, same version
+        # counter).  The renderer keeps references to the caller's tensors while the key is cached, so their storage
+        # cannot be freed and re-allocated to another image at the same address (the ABA case of a key made of
+        # data_ptr alone); writes that bypass the version counter (.data, raw pointers) need invalidate_pyramid().
+        key = tuple((id(t), t.data_ptr(), tuple(t.shape), t.dtype, t._version) for t in ts)
+        if key == self._pyr_key and all(a is b for a, b in zip(ts, self._pyr_held)):
             return self._pyr
         src = []
         for t in ts:
@@ -143,16 +156,27 @@ class B200Renderer:
         _lib.check(self.lib.srf_pack_pyramid(ptrs, Cs, Hs, Ws, fmt, _ptr(self._pyr_buf), nbytes, C.byref(pyr),
                                              _stream_ptr(self.device)))
         self._pyr, self._pyr_key = pyr, key
-        self._pyr_src = src          # keep sources alive until the async pack has certainly run
+        self._pyr_held = ts          # the caller's own tensors (pins their storage while the key is cached)
+        self._pyr_src = src          # fp32 contiguous copies, if any: alive until the async pack has certainly run
         return pyr
+
+    def invalidate_pyramid(self):
+        """Forget the cached feature-pyramid pack (call after writing into x_rgb through .data / raw pointers)."""
+        self._pyr_key = None
+        self._pyr_held = None
+        self._pyr_src = None
 
     def _config(self, cam_K: torch.Tensor, T: Optional[torch.Tensor]) -> Config:
         hp = self.hp
         cfg = Config()
         cfg.dataset = 0 if hp["dataset"] == "kitti" else 1
         n_uni = int(hp["n_pts_uni"])
-        if hp["dataset"] == "bf" and n_uni <= 0:
-            n_uni = 2                                    # scenerf_bf.py:623-626
+        if n_uni <= 0:
+            # scenerf_bf.py:623-626,650-661: with n_pts_uni <= 0 the reference renders the gaussian samples only (a
+            # stand-in n_pts_uni=2 merely provides the view direction).  That sample set is not built here; refuse
+            # loudly (the KITTI class cannot run with it either: torch.linspace(steps=0) -> empty cat at utils.py:86)
+            raise ValueError("n_pts_uni=%d: the gaussian-only sampling branch of scenerf_bf.py:650-661 is not supported"
+                             % n_uni)
         cfg.n_pts_uni = n_uni
         cfg.n_gaussians = int(hp["n_gaussians"])
         cfg.n_pts_per_gaussian = int(hp["n_pts_per_gaussian"])
@@ -319,16 +343,16 @@ class B200Renderer:
         """Diagnostic: raw fp32 TMEM accumulator (ceil(n/128)*128, 512) after `layer` of the tensor-core tile
         program (include/scenerf_b200.h: srf_debug_tc_layer)."""
         net = self._select(mlp)
-        if net.packed is None:
-            raise RuntimeError("renderer was not built with precision='fp16'")
+        if net.packed is None and net.packed_split is None:
+            raise RuntimeError("renderer was not built with precision='fp16' / 'fp32tc'")
         pts = cam_pts.detach().to(device=self.device, dtype=torch.float32).contiguous()
         vd = viewdir.detach().to(device=self.device, dtype=torch.float32).contiguous()
         n_cols, n_per = pts.shape[0], pts.shape[1]
         cfg = self._config(cam_K, None)
-        cfg.precision = _lib.PREC_FP16_TC
         pyr = self._pack_pyramid(x_rgb)
         n = n_cols * n_per
-        acc = torch.zeros(((n + 127) // 128 * 128, 512), dtype=torch.float32, device=self.device)
+        tile = 64 if self.precision == "fp32tc" else 128
+        acc = torch.zeros(((n + tile - 1) // tile * 128, 512), dtype=torch.float32, device=self.device)
         ws = self._workspace(self.lib.srf_predict_workspace_bytes(C.byref(cfg), n))
         _lib.check(self.lib.srf_debug_tc_layer(C.byref(cfg), C.byref(pyr), C.byref(net.struct), _ptr(pts), _ptr(vd),
                                                n_cols, n_per, int(layer), _ptr(acc), _ptr(ws), ws.numel(),

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), "binding and header disagree: %s" % (declared ^ set(_lib.SYMBOLS))
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.srf_abi_version() == 1
+    assert lib.srf_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header_sizes():

@@ -3,23 +3,32 @@ binding) on the same seeded inputs + recorded noise as the reference goldens and
   * the goldens themselves (outputs of the unmodified reference, tests/golden/make_goldens.py), and
   * the CPU oracle for sizes/configs the goldens do not cover.
 Stated tolerances (also in DESIGN.md):
-  fp32 (SIMT) mode : float32 round-off, abs <= 2e-6 + 2e-4 * max(1, |ref|max)
-  fp16 (tcgen05)   : fp16 operands / fp32 accumulate: depth <= 1.5e-3 * max_sample_depth, colour <= 2e-3, other
-                     per-sample quantities <= 1e-2 * max(1, |ref|max)
+  fp32 (SIMT) mode   : float32 round-off, abs <= 2e-6 + 2e-4 * max(1, |ref|max)
+  fp32tc (tcgen05)   : fp16 hi/lo split operands, fp32 accumulate -- float32-grade: the SAME tolerances as fp32
+  fp16 (tcgen05)     : fp16 operands / fp32 accumulate ("fast mode"): depth <= 3e-4 * max_sample_depth (3 cm of 100 m),
+                       colour <= 1e-3, other per-sample quantities <= 1e-2 * max(1, |ref|max)
 Discrete decisions (rounded sphere pixel, arg-min sample, SOM best-matching unit) are compared exactly where the
 implementations agree on the decision and counted where a last-ulp difference flips it."""
 import numpy as np
 import pytest
 
-from cases import RENDER_CASES, PREDICT_CASES, load_golden
+from cases import RENDER_CASES, PREDICT_CASES, load_golden, params_for, pyramid_for
 from helpers import make_renderer, torch_pyramid, max_err
+from oracle import scenerf_oracle as orc          # checker only: arg-max margins of the RaySOM decisions
 
 pytestmark = pytest.mark.gpu
 
 TOL = {
     "fp32": dict(rtol=2e-4, atol=2e-6, depth=2e-4, color=2e-4),
-    "fp16": dict(rtol=1e-2, atol=1e-4, depth=1.5e-3, color=2e-3),
+    "fp32tc": dict(rtol=2e-4, atol=2e-6, depth=2e-4, color=2e-4),
+    "fp16": dict(rtol=1e-2, atol=1e-4, depth=3e-4, color=1e-3),
 }
+PRECS = ["fp32", "fp32tc", "fp16"]
+# RaySOM (ray_som_kl.py:10-78) picks a best-matching prototype per sample.  A ray may differ from the reference only
+# if it contains a sample whose two best prototypes are closer (relative gap of p(z|c)) than the precision mode can
+# resolve: the gap moves with the gaussian means/stds, which carry the mode's MLP error.
+SOM_MARGIN = {"fp32": 1e-3, "fp32tc": 1e-3, "fp16": 0.25}
+SOM_OFF_LIMIT = {"fp32": 0.1, "fp32tc": 0.1, "fp16": 0.3}
 
 
 def _tol(b, prec, scale=None):
@@ -31,7 +40,7 @@ def _np(d):
     return {k: v.detach().cpu().numpy() for k, v in d.items()}
 
 
-@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("name", sorted(RENDER_CASES))
 def test_render_rays_batch_vs_reference_golden(name, prec):
     import torch
@@ -69,17 +78,24 @@ def test_render_rays_batch_vs_reference_golden(name, prec):
     margin = srt[:, 1] - srt[:, 0]
     ok = clean & (margin > 50 * max(d_err, 1e-6))
     assert max_err(out["weights_at_depth"][ok], g["weights_at_depth"][ok]) <= _tol(g["weights"], prec)
-    # RaySOM: arg-max near-ties are round-off decided in the reference itself (see tests/test_oracle.py)
+    # RaySOM: arg-max near-ties are round-off decided in the reference itself (see tests/test_oracle.py): every ray
+    # whose decisions all have a margin must match; rays with a near-tie are counted and bounded
+    pm, pg = params_for(cfg)
+    o = orc.OracleRenderer(cfg, pm, pg)
+    o.render_rays_batch(cfg.K, cfg.T, pyramid_for(cfg, seed), g["pixels"], R, g["noise_u"], g["noise_n"])
+    margin = o.debug["som_margin"]
     bad = np.zeros(R, bool)
     for k in ("loss_kl", "som_vars"):
         err = np.abs(out[k] - g[k]).reshape(R, -1).max(axis=1)
-        bad |= err > _tol(g[k], prec) * (1 if prec == "fp32" else 10)
+        bad |= err > _tol(g[k], prec) * (10 if prec == "fp16" else 1)
     bad &= clean
-    limit = 0.15 if prec == "fp32" else 0.5
-    assert bad.mean() <= limit, "SOM outputs differ on %d of %d rays" % (bad.sum(), R)
+    print("%s/%s: RaySOM outputs off on %d of %d rays (%d of them without a near-tie)" % (
+        name, prec, bad.sum(), R, (bad & (margin > SOM_MARGIN[prec])).sum()))
+    assert not (bad & (margin > SOM_MARGIN[prec])).any(), "SOM outputs differ on rays without an arg-max near-tie"
+    assert bad.mean() <= SOM_OFF_LIMIT[prec], "SOM outputs differ on %d of %d rays" % (bad.sum(), R)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("name", sorted(PREDICT_CASES))
 def test_predict_adversarial_vs_reference_golden(name, prec):
     import torch
