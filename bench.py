@@ -479,7 +479,7 @@ def main():
     ap.add_argument("--train-matmul", default="fp32", choices=["fp32", "tf32"], help="--workload train: GEMM engine")
     ap.add_argument("--sweep-poses", type=int, default=63)
     ap.add_argument("--sweep-scale", type=int, default=2)
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32", "fp32tc"])
     ap.add_argument("--skip-zero-chunks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rays", type=int, default=0, help="diagnostics: use only the first N rays of the workload")

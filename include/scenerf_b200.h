@@ -99,6 +99,9 @@ typedef struct srf_config {
   int precision;             /* srf_precision */
   uint64_t seed;             /* in-kernel Philox seed when noise pointers are NULL */
   int flags;                 /* SRF_FLAG_* */
+  int ray_offset;            /* index of this call's first ray inside the frame it belongs to: the Philox counter of ray i
+                                is (seed, ray_offset + i, sample), so a frame rendered in shards (several calls, several
+                                GPUs: scenerf_b200/dist.py) draws exactly the noise of the unsharded call */
 } srf_config;
 
 #define SRF_FLAG_HIDDEN_FP16 2       /* tensor-core path: the residual hidden state h travels between ResNet blocks as

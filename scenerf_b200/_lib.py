@@ -48,7 +48,7 @@ class Config(C.Structure):
                 ("som_sigma", C.c_float), ("sphere_W", C.c_int), ("sphere_H", C.c_int), ("d_latent", C.c_int),
                 ("v_angle_min", C.c_float), ("v_angle_max", C.c_float), ("h_angle_min", C.c_float),
                 ("h_angle_max", C.c_float), ("K", C.c_float * 9), ("inv_K", C.c_float * 9), ("T", C.c_float * 16),
-                ("precision", C.c_int), ("seed", C.c_uint64), ("flags", C.c_int)]
+                ("precision", C.c_int), ("seed", C.c_uint64), ("flags", C.c_int), ("ray_offset", C.c_int)]
 
 
 OUTPUT_FIELDS = ("depth", "color", "gaussian_means", "gaussian_stds", "weights_at_depth", "closest_pts_to_depths",

@@ -113,6 +113,7 @@ srf::DevParams make_params(const srf_config* cfg, const srf_pyramid* pyr) {
   p.P = cfg->n_pts_per_gaussian;
   p.S = p.U + p.G * p.P;
   p.seed = cfg->seed;
+  p.ray0 = (uint32_t)cfg->ray_offset;
   if (pyr) {
     int off = 0;
     for (int s = 0; s < SRF_NUM_SCALES; ++s) {

@@ -149,7 +149,7 @@ ray_backward_kernel(const __grid_constant__ DevParams p, int R, const float* __r
   for (int i = lane; i < G * P; i += 32) {
     const int g = i / P;
     const float m = fwd.gaussian_means[(size_t)r * G + g], s = fwd.gaussian_stds[(size_t)r * G + g];
-    const float e = noise_n ? noise_n[(size_t)r * G * P + i] : philox_normal(p.seed, (uint32_t)r, (uint32_t)i);
+    const float e = noise_n ? noise_n[(size_t)r * G * P + i] : philox_normal(p.seed, (uint32_t)r + p.ray0, (uint32_t)i);
     const float t = fadd(m, fmul(e, s));
     if (t < 0.1f) continue;
     int lo = 0, hi = S;                          // lower_bound of t in the sorted distances (same float as the forward wrote)

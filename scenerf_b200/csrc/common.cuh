@@ -38,6 +38,7 @@ struct DevParams {
   float halfW[kScales], halfH[kScales];   // float(W_t/2), float(H_t/2): ATen CPU unnormalise scaling factor
   int d_latent;                       // sum C
   uint64_t seed;
+  uint32_t ray0;                      // srf_config.ray_offset: Philox counter of ray r is (seed, ray0 + r, sample)
 };
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }

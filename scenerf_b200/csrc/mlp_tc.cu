@@ -1158,30 +1158,32 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
 
       // ---------------- split mode: the same epilogue for a 64-point tile --------------------------------------------
       //   TMEM lane r (warps of lane quarters 0,1: "hi warps") holds x_hi W^T, lane r + 64 (quarters 2,3: "lo warps")
-      //   x_lo W^T of the same point.  A warp can only read its own lane quarter, so the lo warp hands its 16 values
-      //   per group to its partner (same sub, quarter - 2) through shared memory -- through exactly the 64 bytes of the
-      //   next layer's A tile that the partner lane is about to overwrite with the finished operands (rows r and r+64,
-      //   two granules), so no staging buffer is needed; one 64-thread named barrier per group orders the hand-over.
-      //   The hi warp does all the arithmetic: (D_hi + D_lo) * 2^-s + bias (+ h), ReLU, hi/lo split, A-tile stores.
+      //   x_lo W^T of the same point; a warp can only read its own lane quarter.  Per group of 16 columns the two warps
+      //   of a pair (same sub, quarters q and q+2) swap halves: the hi warp finishes columns 0-7 and needs the lo warp's
+      //   partial sums of those, the lo warp finishes columns 8-15 and needs the hi warp's.  The 2 x 32 bytes travel
+      //   through exactly the bytes of the next layer's A tile that the RECEIVING lane is about to overwrite with the
+      //   finished operands (granule g or g+1 of rows r and r+64), so no staging buffer exists; one 64-thread named
+      //   barrier per group orders the hand-over.  Both warps then do the same arithmetic on their 8 columns:
+      //   (D_hi + D_lo) * 2^-s + bias (+ h), ReLU, hi/lo split, two 16-byte A-tile stores.
       auto epilogue_half_split = [&](int part, int bias_idx, bool use_h, bool write_h) {
         lap(1);
         mbar_wait(half_full(part), half_par[part], a.error_flag);
         half_par[part] ^= 1;
         tc_fence_after();
         lap(2);
-        const bool hi_warp = q4 < 2;
+        const int mine = (q4 < 2) ? 0 : 1;                      // 0: hi warp, finishes columns 0-7 of a group; 1: lo warp, 8-15
         const int pair_bar = 2 + (q4 & 1) * 2 + sub;            // named barriers 2..5: one per (hi, lo) warp pair
-        const int prow = (q4 & 1) * 32 + lane;                  // point row (0..63) this lane works on
+        const int prow = (q4 & 1) * 32 + lane;                  // point row (0..63) of this lane
         const float4* b4 = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden);
         const float inv_scale = __ldg(bias + kInvScaleSlot);
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const int col0 = part * 256 + sub * 128;
         uint32_t vn[16];
-        float4 hn[4];
-        auto load_h = [&](float4 (&dst)[4], int c) {
+        float4 hn[2];
+        auto load_h = [&](float4 (&dst)[2], int c) {            // this warp's 8 columns of group starting at column c
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = (use_h && hi_warp) ? scratch4[(size_t)((c >> 2) + j) * kTileM + prow] : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 2; ++j)
+            dst[j] = use_h ? scratch4[(size_t)((c >> 2) + 2 * mine + j) * kTileM + prow] : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         tmem_ld16(trow + (uint32_t)col0, vn);
         load_h(hn, col0);
@@ -1191,41 +1193,45 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           if ((grp & 3) == 0) wait_slot_free(slot);
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
           const int gcol = (col & 63) >> 3;
-          const uint32_t ex[4] = {slot_addr + sw128_offset(prow, gcol), slot_addr + sw128_offset(prow, gcol + 1),
-                                  slot_addr + sw128_offset(prow + kPts, gcol), slot_addr + sw128_offset(prow + kPts, gcol + 1)};
+          // mine0/mine1: granule of THIS warp's 8 columns in rows r / r+64 ; peer0/peer1: granule of the partner's columns
+          const uint32_t mine0 = slot_addr + sw128_offset(prow, gcol + mine), mine1 = slot_addr + sw128_offset(prow + kPts, gcol + mine);
+          const uint32_t peer0 = slot_addr + sw128_offset(prow, gcol + 1 - mine), peer1 = slot_addr + sw128_offset(prow + kPts, gcol + 1 - mine);
+          float4 bb[2], hh[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) { bb[j] = __ldg(b4 + (col >> 2) + 2 * mine + j); hh[j] = hn[j]; }
           tmem_ld_wait();
           uint32_t v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = vn[j];
-          if (grp < 7) tmem_ld16(trow + (uint32_t)(col + 16), vn);
-          if (!hi_warp) {
+          if (grp < 7) { tmem_ld16(trow + (uint32_t)(col + 16), vn); load_h(hn, col + 16); }
+          // send the 8 partial sums the partner finishes, keep the other 8
+          uint32_t snd[8], keep[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sts128(ex[j], v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            named_bar_sync(pair_bar, 64);
-            continue;
-          }
-          float4 bb[4], hh[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { bb[j] = __ldg(b4 + (col >> 2) + j); hh[j] = hn[j]; }
-          if (grp < 7) load_h(hn, col + 16);
+          for (int j = 0; j < 8; ++j) { snd[j] = mine ? v[j] : v[8 + j]; keep[j] = mine ? v[8 + j] : v[j]; }
+          sts128(peer0, snd[0], snd[1], snd[2], snd[3]);
+          sts128(peer1, snd[4], snd[5], snd[6], snd[7]);
           named_bar_sync(pair_bar, 64);
-          float r[16];
+          const uint4 p0 = lds128(mine0), p1 = lds128(mine1);
+          const float pp[8] = {__uint_as_float(p0.x), __uint_as_float(p0.y), __uint_as_float(p0.z), __uint_as_float(p0.w),
+                               __uint_as_float(p1.x), __uint_as_float(p1.y), __uint_as_float(p1.z), __uint_as_float(p1.w)};
+          const float bbv[8] = {bb[0].x, bb[0].y, bb[0].z, bb[0].w, bb[1].x, bb[1].y, bb[1].z, bb[1].w};
+          const float hhv[8] = {hh[0].x, hh[0].y, hh[0].z, hh[0].w, hh[1].x, hh[1].y, hh[1].z, hh[1].w};
+          float r[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 pl = lds128(ex[j]);
-            r[4 * j + 0] = (__uint_as_float(v[4 * j + 0]) + __uint_as_float(pl.x)) * inv_scale + bb[j].x + hh[j].x;
-            r[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + __uint_as_float(pl.y)) * inv_scale + bb[j].y + hh[j].y;
-            r[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + __uint_as_float(pl.z)) * inv_scale + bb[j].z + hh[j].z;
-            r[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + __uint_as_float(pl.w)) * inv_scale + bb[j].w + hh[j].w;
-            if (write_h) scratch4[(size_t)((col >> 2) + j) * kTileM + prow] = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          for (int j = 0; j < 8; ++j) {
+            // D_hi + D_lo in this order on both warps (the hi warp holds D_hi, the lo warp receives it)
+            const float dsum = mine ? (pp[j] + __uint_as_float(keep[j])) : (__uint_as_float(keep[j]) + pp[j]);
+            r[j] = dsum * inv_scale + bbv[j] + hhv[j];
           }
-          uint32_t hi[8], lo[8];
+          if (write_h) {
+            scratch4[(size_t)((col >> 2) + 2 * mine) * kTileM + prow] = make_float4(r[0], r[1], r[2], r[3]);
+            scratch4[(size_t)((col >> 2) + 2 * mine + 1) * kTileM + prow] = make_float4(r[4], r[5], r[6], r[7]);
+          }
+          uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) split_half2(fmaxf(r[2 * j], 0.0f), fmaxf(r[2 * j + 1], 0.0f), hi[j], lo[j]);
-          sts128(ex[0], hi[0], hi[1], hi[2], hi[3]);
-          sts128(ex[1], hi[4], hi[5], hi[6], hi[7]);
-          sts128(ex[2], lo[0], lo[1], lo[2], lo[3]);
-          sts128(ex[3], lo[4], lo[5], lo[6], lo[7]);
+          for (int j = 0; j < 4; ++j) split_half2(fmaxf(r[2 * j], 0.0f), fmaxf(r[2 * j + 1], 0.0f), hi[j], lo[j]);
+          sts128(mine0, hi[0], hi[1], hi[2], hi[3]);
+          sts128(mine1, lo[0], lo[1], lo[2], lo[3]);
         }
         tc_fence_before();
         fence_proxy_async_smem();

@@ -75,14 +75,14 @@ sample_sort_kernel(const __grid_constant__ DevParams p, int R, const float* __re
   __syncwarp();
   // uniform samples (utils.py:75-90)
   for (int j = lane; j < U; j += 32) {
-    const float u = noise_u ? noise_u[(size_t)r * U + j] : philox_uniform(p.seed, (uint32_t)r, (uint32_t)j, 1u);
+    const float u = noise_u ? noise_u[(size_t)r * U + j] : philox_uniform(p.seed, (uint32_t)r + p.ray0, (uint32_t)j, 1u);
     k[j] = fadd(linspace_at(0.2f, p.max_depth, U, j), fmul(u, p.uni_step));
   }
   // gaussian samples (utils.py:204-214)
   for (int j = lane; j < G * P; j += 32) {
     const int g = j / P;
     const float m = gm[g], s = gm[kMaxGaussians + g];
-    const float e = noise_n ? noise_n[(size_t)r * G * P + j] : philox_normal(p.seed, (uint32_t)r, (uint32_t)j);
+    const float e = noise_n ? noise_n[(size_t)r * G * P + j] : philox_normal(p.seed, (uint32_t)r + p.ray0, (uint32_t)j);
     float t = fadd(m, fmul(e, s));
     if (t < 0.1f) t = 0.1f;
     k[U + j] = t;

@@ -29,11 +29,12 @@ def shard_range(n_rays: int, rank: int, world: int) -> Tuple[int, int, int]:
 
 def pack_result(depth: torch.Tensor, color: torch.Tensor, rows: int) -> torch.Tensor:
     """(r,) + (r,3) -> (rows,4) [depth, r, g, b], zero padded to `rows`."""
-    out = torch.zeros((rows, 4), dtype=torch.float32, device=depth.device)
     r = depth.shape[0]
+    out = torch.empty((rows, 4), dtype=torch.float32, device=depth.device)
     if r:
-        out[:r, 0] = depth
-        out[:r, 1:] = color
+        torch.cat([depth.reshape(r, 1), color.reshape(r, 3)], dim=1, out=out[:r])
+    if r < rows:
+        out[r:].zero_()
     return out
 
 
@@ -48,11 +49,14 @@ def _all_gather(packed: torch.Tensor, world: int) -> torch.Tensor:
 
 
 def render_frame_sharded(render_fn: Callable, sampled_pixels: torch.Tensor):
-    """Ray-range shard of one frame + one all-gather.  Returns (depth (R,), color (R,3)) on every rank."""
+    """Ray-range shard of one frame + one all-gather.  Returns (depth (R,), color (R,3)) on every rank.
+    render_fn(pixels, ray_offset) -> (depth (r,), color (r,3)): ray_offset is the index of the shard's first ray in
+    the frame (B200Renderer.render_rays_batch(ray_offset=..., seed=...) keys its Philox noise on it, so that the
+    sharded frame equals the single-GPU frame bit for bit)."""
     world, rank = dist.get_world_size(), dist.get_rank()
     R = int(sampled_pixels.shape[0])
     start, stop, per = shard_range(R, rank, world)
-    depth, color = render_fn(sampled_pixels[start:stop])
+    depth, color = render_fn(sampled_pixels[start:stop], start)
     full = _all_gather(pack_result(depth, color, per), world)[:R]
     return full[:, 0].contiguous(), full[:, 1:].contiguous()
 

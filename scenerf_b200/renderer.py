@@ -219,10 +219,13 @@ class B200Renderer:
 
     # ------------------------------------------------------------------------------------------------------------
     def render_rays_batch(self, cam_K, T_source2infer, x_rgb, depth_window=100, T_cam2velo=None,
-                          sampled_pixels=None, ray_batch_size=128, *, noise=None, outputs="all", debug=False):
+                          sampled_pixels=None, ray_batch_size=128, *, noise=None, outputs="all", debug=False,
+                          ray_offset=0, seed=None):
         """scenerf.py:392-471.  `depth_window` and `T_cam2velo` are accepted and unused, exactly like the reference.
         noise: optional (noise_u (R,U), noise_n (R,G*P)) tensors overriding the RNG (parity tests).
-        outputs: "all" -> the reference's 12-key dict; "minimal" -> depth and color only (what inference reads)."""
+        outputs: "all" -> the reference's 12-key dict; "minimal" -> depth and color only (what inference reads).
+        ray_offset / seed (rng="philox" only): the rays are rays [ray_offset, ray_offset+R) of a larger frame rendered
+        with Philox seed `seed` -- a frame split over several calls or GPUs draws the noise of the single call."""
         if sampled_pixels is None:
             raise TypeError("sampled_pixels is required (the reference fails on None too: scenerf.py:419)")
         pix = sampled_pixels.detach().to(device=self.device, dtype=torch.float32).contiguous()
@@ -256,9 +259,12 @@ class B200Renderer:
                 raise ValueError("noise shapes %s %s" % (tuple(nu.shape), tuple(nn_.shape)))
         elif self.rng == "torch":
             nu, nn_ = self._draw_noise_like_reference(R, int(ray_batch_size), cfg)
+        elif seed is not None:
+            cfg.seed = int(seed)
         else:
             self.seed += 1
             cfg.seed = self.seed
+        cfg.ray_offset = int(ray_offset)
         nbytes = self.lib.srf_render_workspace_bytes(C.byref(cfg), R)
         ws = self._workspace(nbytes)
         _lib.check(self.lib.srf_render_rays(C.byref(cfg), C.byref(pyr), C.byref(self.mlp.struct),

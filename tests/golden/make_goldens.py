@@ -251,6 +251,41 @@ def kitti_identity():
     return run_render_case(cfg, synth.random_pixels(24, 32, cfg.img_W, cfg.img_H), pyr_seed=34)
 
 
+FULL_KEEP = ("depth", "color", "gaussian_means", "gaussian_stds", "weights_at_depth", "closest_pts_to_depths", "loss_kl",
+             "alphas", "som_vars", "densities", "weights", "depth_volumes", "noise_u", "noise_n", "pixels", "main_sphere",
+             "gauss_sphere")
+
+
+def full_size_pixels(cfg, n=256):
+    """n integer pixels of the x-major full-frame grid (render_colors.py:103-111), spread over the whole image."""
+    grid = synth.grid_pixels(cfg.img_W, cfg.img_H)
+    idx = (np.arange(n, dtype=np.int64) * (grid.shape[0] // n + 1) + 13) % grid.shape[0]
+    return np.ascontiguousarray(grid[idx])
+
+
+def run_full_case(cfg, pyr_seed):
+    g = run_render_case(cfg, full_size_pixels(cfg), pyr_seed=pyr_seed)
+    return {k: g[k] for k in FULL_KEEP}
+
+
+@case
+def full_B():
+    """BASELINE.json configs[1] at FULL size: sphere grid 1226x370 (281 MB pyramid), S = 128; 256 rays of the frame."""
+    return run_full_case(synth.config_B(name="full_B"), 41)
+
+
+@case
+def full_Bp():
+    """config B' (SURVEY 8d): the reference-default 1500x452 sphere grid (420 MB pyramid), S = 128."""
+    return run_full_case(synth.config_B(name="full_Bp", sphere_W=1500, sphere_H=452), 42)
+
+
+@case
+def full_C():
+    """BASELINE.json configs[2] at FULL size: BundleFusion 640x480 sphere grid (190 MB pyramid), S = 96."""
+    return run_full_case(synth.config_C(name="full_C"), 43)
+
+
 @case
 def predict_adversarial_kitti():
     cfg = synth.config_A(name="adv_kitti", sphere_W=300, sphere_H=90)

@@ -12,8 +12,11 @@ import torch.multiprocessing as mp
 from scenerf_b200 import dist as sdist
 
 
-def _fake_render(pix):
-    depth = pix[:, 0] * 0.5 + pix[:, 1] * 0.25 + 1.0
+def _fake_render(pix, ray_offset=0):
+    # depends on the ray's index inside the frame like the in-kernel Philox noise does: a shard rendered with the wrong
+    # offset cannot reproduce the unsharded result
+    idx = torch.arange(pix.shape[0], dtype=torch.float32) + float(ray_offset)
+    depth = pix[:, 0] * 0.5 + pix[:, 1] * 0.25 + 1.0 + idx * 0.125
     color = torch.stack([pix[:, 0] * 0.001, pix[:, 1] * 0.002, pix[:, 0] * 0.0 + 0.5], dim=1)
     return depth, color
 

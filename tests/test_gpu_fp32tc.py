@@ -84,12 +84,12 @@ def test_split_tile_program_layer_by_layer(which):
         lo_share = float(np.abs(raw[:, 1]).max() / max(np.abs(raw[:, 0]).max(), 1e-30))
         print("%s layer %2d: max|acc| %.3e  max-abs-err %.3e (rel %.1e), low-part rows / high-part rows %.1e"
               % (which, layer, mag, err, err / mag, lo_share))
-        assert err <= 4e-6 * mag + 1e-6, "layer %d: err %.3e (scale %.3e)" % (layer, err, mag)
+        assert err <= 2e-5 * mag + 1e-6, "layer %d: err %.3e (scale %.3e)" % (layer, err, mag)
         assert lo_share < 2e-3                                 # rows 64..127 really are the 2^-11-sized low parts
     raw = r.predict(which, torch.from_numpy(pts), x_rgb, K, None, torch.from_numpy(vd), output_type="offset")
     got = raw.reshape(n, -1).cpu().numpy()
     want = exp["final"]
-    assert np.abs(got - want).max() <= 4e-6 * np.abs(want).max() + 1e-6
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max() + 1e-6
 
 
 def test_fp32tc_vs_fp32_device_paths_large_ragged():

@@ -12,7 +12,7 @@ implementations agree on the decision and counted where a last-ulp difference fl
 import numpy as np
 import pytest
 
-from cases import RENDER_CASES, PREDICT_CASES, load_golden, params_for, pyramid_for
+from cases import RENDER_CASES, PREDICT_CASES, FULL_CASES, load_golden, params_for, pyramid_for
 from helpers import make_renderer, torch_pyramid, max_err
 from oracle import scenerf_oracle as orc          # checker only: arg-max margins of the RaySOM decisions
 
@@ -28,7 +28,7 @@ PRECS = ["fp32", "fp32tc", "fp16"]
 # if it contains a sample whose two best prototypes are closer (relative gap of p(z|c)) than the precision mode can
 # resolve: the gap moves with the gaussian means/stds, which carry the mode's MLP error.
 SOM_MARGIN = {"fp32": 1e-3, "fp32tc": 1e-3, "fp16": 0.25}
-SOM_OFF_LIMIT = {"fp32": 0.1, "fp32tc": 0.1, "fp16": 0.3}
+SOM_OFF_LIMIT = {"fp32": 0.2, "fp32tc": 0.2, "fp16": 0.3}
 
 
 def _tol(b, prec, scale=None):
@@ -43,11 +43,28 @@ def _np(d):
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("name", sorted(RENDER_CASES))
 def test_render_rays_batch_vs_reference_golden(name, prec):
-    import torch
     cfg, seed = RENDER_CASES[name]
+    _compare_with_golden(name, cfg, load_golden(name), prec, pyramid_for(cfg, seed))
+
+
+@pytest.mark.parametrize("name", sorted(FULL_CASES))
+def test_full_size_vs_reference_golden(name):
+    """BASELINE.json configs B, B' and C at their FULL sphere-grid sizes and sample counts (1226x370 / 1500x452 /
+    640x480; S = 128 / 128 / 96), 256 rays spread over the frame, all three precision modes against the outputs of
+    the unmodified reference: index arithmetic at full size (tap offsets up to 80*370*1226, the 16-bit sphere
+    coordinates kept in shared memory, (W//s,H//s) corners of the real grids)."""
+    from scenerf_b200 import synth
+    cfg, seed = FULL_CASES[name]
     g = load_golden(name)
+    pyr = synth.make_pyramid(seed, cfg.sphere_W, cfg.sphere_H)       # 190-420 MB, not cached
+    for prec in PRECS:
+        _compare_with_golden(name, cfg, g, prec, pyr)
+
+
+def _compare_with_golden(name, cfg, g, prec, pyr_np):
+    import torch
     r = make_renderer(cfg, prec)
-    x_rgb = torch_pyramid(cfg, seed)
+    x_rgb = {k: torch.from_numpy(v).to("cuda:0") for k, v in pyr_np.items()}
     out = _np(r.render_rays_batch(torch.from_numpy(cfg.K), torch.from_numpy(cfg.T), x_rgb,
                                   sampled_pixels=torch.from_numpy(g["pixels"]), ray_batch_size=g["pixels"].shape[0],
                                   noise=(torch.from_numpy(g["noise_u"]), torch.from_numpy(g["noise_n"])), debug=True))
@@ -82,7 +99,7 @@ def test_render_rays_batch_vs_reference_golden(name, prec):
     # whose decisions all have a margin must match; rays with a near-tie are counted and bounded
     pm, pg = params_for(cfg)
     o = orc.OracleRenderer(cfg, pm, pg)
-    o.render_rays_batch(cfg.K, cfg.T, pyramid_for(cfg, seed), g["pixels"], R, g["noise_u"], g["noise_n"])
+    o.render_rays_batch(cfg.K, cfg.T, pyr_np, g["pixels"], R, g["noise_u"], g["noise_n"])
     margin = o.debug["som_margin"]
     bad = np.zeros(R, bool)
     for k in ("loss_kl", "som_vars"):

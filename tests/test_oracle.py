@@ -6,7 +6,7 @@ Tolerances are float32 round-off of a different libm / BLAS summation order, sta
 import numpy as np
 import pytest
 
-from cases import RENDER_CASES, PREDICT_CASES, load_golden, pyramid_for, params_for
+from cases import RENDER_CASES, PREDICT_CASES, FULL_CASES, load_golden, pyramid_for, params_for
 from oracle import scenerf_oracle as orc
 from scenerf_b200 import synth
 
@@ -79,7 +79,28 @@ def test_render_rays_batch_vs_reference(name):
     _check_som(out, g, clean, o.debug["som_margin"])
 
 
-def _check_som(out, g, clean, margin, rtol=1e-4):
+@pytest.mark.parametrize("name", sorted(FULL_CASES))
+def test_render_rays_batch_full_size_vs_reference(name):
+    """The oracle at the FULL sizes of BASELINE.json configs B / B' / C (256 rays of the frame) against the reference's
+    own outputs: pins the restatement where bench.py's in-run parity check and the GPU full-size tests use it."""
+    cfg, seed = FULL_CASES[name]
+    g = load_golden(name)
+    pm, pg = params_for(cfg)
+    o = orc.OracleRenderer(cfg, pm, pg)
+    out = o.render_rays_batch(cfg.K, cfg.T, synth.make_pyramid(seed, cfg.sphere_W, cfg.sphere_H), g["pixels"],
+                              g["pixels"].shape[0], g["noise_u"], g["noise_n"])
+    flips_main = (o.debug["main_sphere"] != g["main_sphere"]).any(axis=1).reshape(-1, cfg.S).any(axis=1)
+    flips_gauss = (o.debug["gauss_sphere"] != g["gauss_sphere"]).any(axis=1).reshape(-1, cfg.n_gaussians).any(axis=1)
+    clean = ~(flips_main | flips_gauss)
+    assert clean.mean() > 0.98, "too many sphere-pixel rounding flips: %d rays" % (~clean).sum()
+    for k in ("depth", "color", "gaussian_means", "gaussian_stds", "alphas", "densities", "weights", "depth_volumes"):
+        _close(out[k][clean], g[k][clean], k)
+    # 256 rays x 96-128 samples: one BundleFusion ray (som_sigma = 0.02, exponents of ~1e3) sits at a relative gap of
+    # 5e-4 and moves loss_kl by 1e-3 relative -- the near-tie bound is 1e-3 here
+    _check_som(out, g, clean, o.debug["som_margin"], margin_thr=1e-3)
+
+
+def _check_som(out, g, clean, margin, rtol=1e-4, margin_thr=1e-5):
     """loss_kl / som_vars (ray_som_kl.py:10-78) hinge on a per-sample arg-max over prototypes.  For samples far from
     every gaussian all candidates are equal up to the last ulp of exp(), so the reference's own choice there is
     round-off; a ray may disagree only if it contains such a (near-)tie, and only a small fraction may."""
@@ -90,7 +111,7 @@ def _check_som(out, g, clean, margin, rtol=1e-4):
         err = np.abs(a - b).reshape(a.shape[0], -1).max(axis=1)
         bad |= err > tol
     bad &= clean
-    assert not (bad & (margin > 1e-5)).any(), "SOM outputs differ on rays without an arg-max near-tie"
+    assert not (bad & (margin > margin_thr)).any(), "SOM outputs differ on rays without an arg-max near-tie"
     assert bad.mean() <= 0.1, "SOM outputs differ on %d of %d rays" % (bad.sum(), bad.size)
 
 
