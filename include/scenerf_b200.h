@@ -79,6 +79,8 @@ typedef struct srf_pyramid {
   const void* hwc[SRF_NUM_SCALES];   /* [H][W][C] of float (format 0) or IEEE half (format 1) */
   int C[SRF_NUM_SCALES], H[SRF_NUM_SCALES], W[SRF_NUM_SCALES];
   int format;                        /* srf_pyramid_format */
+  const void* latent_table;          /* optional: srf_build_latent_table() output for the MAIN network (`mlp`), else NULL */
+  int latent_table_format;           /* srf_pyramid_format of the table rows: FP16 is used by SRF_PREC_FP16_TC, FP32 by SRF_PREC_FP32_TC */
 } srf_pyramid;
 
 /* Hyper-parameters the path reads from the module (scenerf.py:23-115) + per-call camera and pose. */
@@ -159,6 +161,19 @@ int srf_pack_weights_tc(const srf_mlp_weights* w, void* dst_dev, size_t dst_byte
  * [2^13, 2^14), exact, undone in the epilogues) and stored as two fp16 images, hi = rn(w 2^s) and lo = rn(w 2^s - hi). */
 size_t srf_tc_split_weights_bytes(int d_out, int d_latent);
 int srf_pack_weights_tc_split(const srf_mlp_weights* w, void* dst_dev, size_t dst_bytes, void* stream);
+
+/* Pre-projected latents (optional, once per image and network).  SphericalMapping.from_pixels rounds the sphere
+ * coordinates to integers (spherical_mapping.py:115), so the 2480-channel latent of a sample point -- and therefore
+ * lin_z[b](z) of resnetfc.py:148-150 -- is a function of the integer sphere pixel only.  The table holds
+ * lin_z[b].weight . z(pixel) (3 x 512 values) for every pixel that can have a valid bilinear tap (+ one zero row); with
+ * `pyr->latent_table` set, the tensor-core modes skip the three lin_z GEMM passes of the MAIN network (70.5 % of the
+ * per-point FLOPs) and add the table row in the epilogue.  Exact in real arithmetic; rounding differs from the dense
+ * path at float32 round-off (fp32 table) / fp16 round-off (fp16 table).  pyr must be an SRF_PYR_FP32 pack.
+ * Sizes: table (sphere_W+1)*(sphere_H+1)*1536 values (config B: 1.4 GB fp16 / 2.8 GB fp32); workspace 2 KB per texel. */
+size_t srf_latent_table_bytes(const srf_config* cfg, int format);
+size_t srf_latent_table_workspace_bytes(const srf_pyramid* pyr);
+int srf_build_latent_table(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w_main, int format,
+                           void* table_dev, size_t table_bytes, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* --- the hot path ----------------------------------------------------------------------------------------- */
 size_t srf_render_workspace_bytes(const srf_config* cfg, int n_rays);

@@ -39,7 +39,8 @@ class MlpWeights(C.Structure):
 
 class Pyramid(C.Structure):
     _fields_ = [("hwc", C.c_void_p * NUM_SCALES), ("C", C.c_int * NUM_SCALES), ("H", C.c_int * NUM_SCALES),
-                ("W", C.c_int * NUM_SCALES), ("format", C.c_int)]
+                ("W", C.c_int * NUM_SCALES), ("format", C.c_int), ("latent_table", C.c_void_p),
+                ("latent_table_format", C.c_int)]
 
 
 class Config(C.Structure):
@@ -76,6 +77,10 @@ SYMBOLS = {
     "srf_pack_weights_tc": (C.c_int, [C.POINTER(MlpWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
     "srf_tc_split_weights_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "srf_pack_weights_tc_split": (C.c_int, [C.POINTER(MlpWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "srf_latent_table_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int]),
+    "srf_latent_table_workspace_bytes": (C.c_size_t, [C.POINTER(Pyramid)]),
+    "srf_build_latent_table": (C.c_int, [C.POINTER(Config), C.POINTER(Pyramid), C.POINTER(MlpWeights), C.c_int, C.c_void_p,
+                                         C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "srf_render_workspace_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int]),
     "srf_render_rays": (C.c_int, [C.POINTER(Config), C.POINTER(Pyramid), C.POINTER(MlpWeights), C.POINTER(MlpWeights),
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Outputs), C.c_void_p,

@@ -131,6 +131,8 @@ srf::DevParams make_params(const srf_config* cfg, const srf_pyramid* pyr) {
     }
     p.ch_off[SRF_NUM_SCALES] = off;
     p.d_latent = off;
+    p.preproj = pyr->latent_table;
+    p.preproj_fp16 = pyr->latent_table_format == SRF_PYR_FP16;
   }
   return p;
 }
@@ -161,9 +163,12 @@ int run_mlp(const srf::DevParams& p, int precision, int flags, const srf_mlp_wei
   if (precision == SRF_PREC_FP32 && saved)
     l = srf::run_point_mlp_forward_save(p, w, pts, viewdir, n, n_per, raw, dbg, saved, (flags & SRF_FLAG_TF32_MATMUL) ? 1 : 0, ws, ws_bytes, st);
   else if (precision == SRF_PREC_FP32) l = srf::run_point_mlp_simt(p, w, pts, viewdir, n, n_per, raw, dbg, ws, ws_bytes, st);
-  else
-    l = srf::run_point_mlp_tc(p, w, pts, viewdir, n, n_per, raw, dbg,
-                              precision == SRF_PREC_FP32_TC ? (flags | srf::kTcFlagSplit) : (flags & ~srf::kTcFlagSplit), ws, ws_bytes, st);
+  else {
+    int f = flags & ~(srf::kTcFlagSplit | srf::kTcFlagPreproj);
+    if (precision == SRF_PREC_FP32_TC) f |= srf::kTcFlagSplit;
+    if (w.d_out == 4) f |= srf::kTcFlagPreproj;               // the latent table belongs to the main network
+    l = srf::run_point_mlp_tc(p, w, pts, viewdir, n, n_per, raw, dbg, f, ws, ws_bytes, st);
+  }
   if (l < 0) return fail(SRF_E_WORKSPACE, "point-MLP workspace too small (%zu bytes)", ws_bytes);
   prof_record(2 * pass + 1, st);
   g_launches += l;
@@ -257,6 +262,8 @@ int srf_pack_pyramid(const float* const* chw_dev, const int* C, const int* H, co
     return fail(SRF_E_WORKSPACE, "srf_pack_pyramid: dst has %zu bytes, need %zu", dst_bytes, srf_pyramid_bytes(C, H, W, format));
   const size_t esz = format == SRF_PYR_FP16 ? 2 : 4;
   out->format = format;
+  out->latent_table = nullptr;
+  out->latent_table_format = 0;
   unsigned char* d = reinterpret_cast<unsigned char*>(dst_dev);
   for (int s = 0; s < SRF_NUM_SCALES; ++s) {
     if (!chw_dev[s] || C[s] < 1 || H[s] < 1 || W[s] < 1) return fail(SRF_E_INVALID, "srf_pack_pyramid: scale %d empty", s);
@@ -289,6 +296,34 @@ int srf_pack_weights_tc_split(const srf_mlp_weights* w, void* dst_dev, size_t ds
 
 int srf_pack_weights_tc(const srf_mlp_weights* w, void* dst_dev, size_t dst_bytes, void* stream) {
   return pack_tc_common(w, dst_dev, dst_bytes, 0, stream, "srf_pack_weights_tc");
+}
+
+size_t srf_latent_table_bytes(const srf_config* cfg, int format) {
+  if (!cfg || cfg->sphere_W < 1 || cfg->sphere_H < 1) return 0;
+  return srf::preproj_table_bytes(cfg->sphere_W, cfg->sphere_H, format == SRF_PYR_FP16);
+}
+size_t srf_latent_table_workspace_bytes(const srf_pyramid* pyr) { return pyr ? srf::preproj_workspace_bytes(pyr->H, pyr->W) : 0; }
+
+int srf_build_latent_table(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w_main, int format,
+                           void* table_dev, size_t table_bytes, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  if (int rc = validate(cfg, pyr)) return rc;
+  if (!pyr || !w_main || !table_dev || !workspace_dev) return fail(SRF_E_INVALID, "srf_build_latent_table: NULL argument");
+  if (pyr->format != SRF_PYR_FP32) return fail(SRF_E_INVALID, "srf_build_latent_table: needs an SRF_PYR_FP32 pyramid");
+  if (format != SRF_PYR_FP32 && format != SRF_PYR_FP16) return fail(SRF_E_INVALID, "srf_build_latent_table: format %d", format);
+  const int d_latent = pyramid_channels(pyr);
+  if (int rc = validate_weights(w_main, w_main->d_out, d_latent, SRF_PREC_FP32)) return rc;
+  if (table_bytes < srf_latent_table_bytes(cfg, format) || workspace_bytes < srf_latent_table_workspace_bytes(pyr))
+    return fail(SRF_E_WORKSPACE, "srf_build_latent_table: table %zu / workspace %zu bytes, need %zu / %zu", table_bytes, workspace_bytes,
+                srf_latent_table_bytes(cfg, format), srf_latent_table_workspace_bytes(pyr));
+  srf_pyramid plain = *pyr;
+  plain.latent_table = nullptr;
+  const srf::DevParams p = make_params(cfg, &plain);
+  const int l = srf::run_preproject(p, *w_main, format == SRF_PYR_FP16, table_dev, table_bytes, workspace_dev, workspace_bytes,
+                                    (cudaStream_t)stream);
+  if (l < 0) return fail(SRF_E_INVALID, "srf_build_latent_table: unsupported shape");
+  g_launches = l;
+  return check_cuda("srf_build_latent_table");
 }
 
 size_t srf_render_workspace_bytes(const srf_config* cfg, int n_rays) {

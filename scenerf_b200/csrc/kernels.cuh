@@ -90,11 +90,19 @@ void launch_ray_backward(const DevParams& p, int R, const float* raw, const floa
 //   split != 0: the fp32-grade layout (hi + lo fp16 images of W 2^s, see mlp_tc.cu) read through w.tc_split_packed
 size_t tc_weights_bytes(int d_out, int d_latent, int split);
 int pack_weights_tc(const srf_mlp_weights& w, void* dst, size_t bytes, int split, cudaStream_t st);
+constexpr int kTcFlagPreproj = 1 << 29; // internal bit: this pass may use DevParams::preproj (the table of ITS network)
 constexpr int kTcFlagSplit = 1 << 30;   // internal bit of the `flags` argument of run_point_mlp_tc*: split (fp32-grade) mode
 size_t tc_workspace_bytes(int d_latent, int n_points);
 int run_point_mlp_tc(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n,
                      int n_per, float* raw_out, int32_t* dbg_sphere, int flags, void* workspace, size_t ws_bytes,
                      cudaStream_t st);
+
+// preproj.cu : pre-projected latent table  table[(sy,sx)][block][512] = lin_z[block].weight . z(sphere pixel)  (see file header)
+size_t preproj_rows(int sphere_W, int sphere_H);
+size_t preproj_table_bytes(int sphere_W, int sphere_H, int fp16);
+size_t preproj_workspace_bytes(const int* H, const int* W);
+int run_preproject(const DevParams& p, const srf_mlp_weights& w, int fp16, void* table, size_t table_bytes, void* workspace,
+                   size_t ws_bytes, cudaStream_t st);
 
 // non-zero after the kernel's mbarrier watchdog fired: 0x40000000 | warp<<24 | (barrier smem offset)<<4 | parity
 int tc_watchdog_flag();

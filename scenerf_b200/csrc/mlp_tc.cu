@@ -89,6 +89,9 @@ struct KernelArgs {
   int skip_zero;           // SRF_FLAG_SKIP_ZERO_CHUNKS
   int hidden_fp16;         // SRF_FLAG_HIDDEN_FP16: the hidden state travels between blocks as fp16 (scratch bytes halved)
   int split;               // fp32-grade mode: 64 points per tile, A rows 0-63 = fp16 hi parts, rows 64-127 = lo parts; hi+lo weight images
+  const unsigned char* preproj;  // pre-projected latent table (preproj.cu) or null: rows of 3 x 512 values (fp16 in fp16 mode, fp32 in
+                                 // split mode); when set, the lin_z GEMMs are not executed and E1 adds the row of the point's sphere pixel
+  int pre_W1, pre_H1;      // sphere_W + 1, sphere_H + 1: row = sy * pre_W1 + sx inside, pre_W1 * pre_H1 (the zero row) outside
   int use_tmap;            // CTA pairs: weight images by cp.async.bulk.tensor.cta_group::2 that signals the LEADER's barrier
   int debug_layer;         // -1, or: stop every tile after this layer's ACC is complete and dump it
   float* debug_acc;        // (n_tiles*128, 512)
@@ -533,7 +536,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       } prod{images, smem_base, bar0, kz, crank, a.error_flag, Ring(), l2_policy_evict_last(), &tm_main, &tm_out, a.use_tmap != 0};
       uint32_t meta_phase = 0;
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
-        uint64_t mask = ~0ull;
+        uint64_t mask = a.preproj ? 0ull : ~0ull;              // pre-projected latents: no lin_z chunk is executed
         if (a.skip_zero) {
           mbar_wait(meta_full, meta_phase, a.error_flag);        // this tile group's chunk mask is published
           meta_phase ^= 1;
@@ -635,7 +638,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             make_idesc(kTileM * CG, kMmaN), make_idesc(kTileM * CG, kOutN), 0, 0, PROF && a.prof != nullptr};
       uint32_t meta_phase = 0;
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
-        uint64_t mask = ~0ull;
+        uint64_t mask = a.preproj ? 0ull : ~0ull;
         if (a.skip_zero) {
           mbar_wait(meta_full, meta_phase, a.error_flag);
           meta_phase ^= 1;
@@ -665,7 +668,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       } rel{bar0, a.error_flag, Ring()};
       uint32_t meta_phase = 0;
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
-        uint64_t mask = ~0ull;
+        uint64_t mask = a.preproj ? 0ull : ~0ull;
         if (a.skip_zero) {
           mbar_wait(meta_full, meta_phase, a.error_flag);
           meta_phase ^= 1;
@@ -753,7 +756,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       };
       if (it == 0 || a.debug_layer >= 0) geometry(grp_i, it);
       const short2* sph_cur = sph_smem + (it & 1) * kTileM;
-      uint64_t mask = ~0ull;
+      uint64_t mask = a.preproj ? 0ull : ~0ull;
       if (a.skip_zero) {
         if (wt == 0) mask_smem[(it + 1) & 1] = 0ull;          // buffer of the NEXT tile group (filled later in this tile)
         mbar_wait(meta_full, meta_phase, a.error_flag);
@@ -761,6 +764,14 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         mask = mask_smem[it & 1];
       }
       named_bar_sync(1, kWorkerThreads);          // sph_smem visible to all workers
+      // pre-projected latents: table row of the point this lane finishes in the epilogues (zero row outside the grid)
+      const unsigned char* pre_row = nullptr;
+      if (a.preproj) {
+        const short2 sp = sph_cur[SPLIT ? ((q4 & 1) * 32 + lane) : erow];
+        const bool in = sp.x >= 0 && sp.x < a.pre_W1 && sp.y >= 0 && sp.y < a.pre_H1;
+        const size_t ridx = in ? (size_t)sp.y * a.pre_W1 + sp.x : (size_t)a.pre_W1 * a.pre_H1;
+        pre_row = a.preproj + ridx * (size_t)(SRF_NUM_BLOCKS * kHidden * (SPLIT ? 4 : 2));
+      }
 
       // ---------------- L0: x chunk = [pe(39) | viewdir(3) | 0] as fp16 (FIFO slot) ---------------------------
       {
@@ -827,6 +838,14 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             const short2 sp16 = sph_cur[xrow];
             const int2 sp = make_int2(sp16.x, sp16.y);
             const int esz = p.feat_fp16 ? 2 : 4;
+            if (a.preproj) {
+              // warm L2 with this point's table row (3 x 512 values): the E1 epilogues read it thousands of cycles later
+              if (sp.x >= 0 && sp.x < a.pre_W1 && sp.y >= 0 && sp.y < a.pre_H1) {
+                constexpr int kRowBytes = SRF_NUM_BLOCKS * kHidden * (SPLIT ? 4 : 2);
+                const unsigned char* rowp = a.preproj + ((size_t)sp.y * a.pre_W1 + sp.x) * kRowBytes;
+                for (int b = 0; b < kRowBytes; b += 128) prefetch_l2(rowp + b);
+              }
+            } else
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
               const Taps tp = scale_taps(p, s, sp.x, sp.y);
@@ -1088,12 +1107,19 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             for (int j = 0; j < 4; ++j) dst[j] = scratch4[(size_t)((c >> 2) + j) * kTileM + erow];
           }
         };
+        // pre-projected latents (E1 only: write_h): 16 fp16 table values of this row per group, loaded one group ahead
+        const bool use_p = write_h && pre_row != nullptr;
+        const uint4* prow16 = reinterpret_cast<const uint4*>(pre_row + (size_t)bias_idx * kHidden * 2);
+        uint4 pn[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+        if (use_p) { pn[0] = __ldg(prow16 + (col0 >> 3)); pn[1] = __ldg(prow16 + (col0 >> 3) + 1); }
         tmem_ld16(trow + (uint32_t)col0, vn);
         load_h(hx, col0);
         load_h(hy, col0 + 16);
         auto process = [&](int grp, float4 (&hbuf)[4]) {
           const int col = col0 + grp * 16;
           float4 bb[4], hh[4];
+          const uint4 pc0 = pn[0], pc1 = pn[1];
+          if (use_p && grp < 7) { pn[0] = __ldg(prow16 + ((col + 16) >> 3)); pn[1] = __ldg(prow16 + ((col + 16) >> 3) + 1); }
 #pragma unroll
           for (int j = 0; j < 4; ++j) bb[j] = __ldg(b4 + (col >> 2) + j);   // 16 KB bias header: L1-resident broadcast
           tmem_ld_wait();
@@ -1131,6 +1157,12 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
               r[half].y = __uint_as_float(v[j * 4 + 1]) + bb[j].y + hh[j].y;
               r[half].z = __uint_as_float(v[j * 4 + 2]) + bb[j].z + hh[j].z;
               r[half].w = __uint_as_float(v[j * 4 + 3]) + bb[j].w + hh[j].w;
+              if (use_p) {
+                const uint4 pq = gq ? pc1 : pc0;                  // 8 halves of granule gq; this float4 = words (2*half, 2*half+1)
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(half ? &pq.z : &pq.x));
+                const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(half ? &pq.w : &pq.y));
+                r[half].x += f0.x; r[half].y += f0.y; r[half].z += f1.x; r[half].w += f1.y;
+              }
               if (write_h && !h16) scratch4[(size_t)((col >> 2) + j) * kTileM + erow] = r[half];
             }
             if (write_h && h16)
@@ -1185,11 +1217,17 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           for (int j = 0; j < 2; ++j)
             dst[j] = use_h ? scratch4[(size_t)((c >> 2) + 2 * mine + j) * kTileM + prow] : make_float4(0.f, 0.f, 0.f, 0.f);
         };
+        const bool use_p = write_h && pre_row != nullptr;       // pre-projected latents: 8 fp32 table values per group, one group ahead
+        const float4* prow32 = reinterpret_cast<const float4*>(pre_row + (size_t)bias_idx * kHidden * 4);
+        float4 pn[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+        if (use_p) { pn[0] = __ldg(prow32 + (col0 >> 2) + 2 * mine); pn[1] = __ldg(prow32 + (col0 >> 2) + 2 * mine + 1); }
         tmem_ld16(trow + (uint32_t)col0, vn);
         load_h(hn, col0);
         for (int grp = 0; grp < 8; ++grp) {
           const int col = col0 + grp * 16;
           const int slot = col >> 6;
+          const float ppv[8] = {pn[0].x, pn[0].y, pn[0].z, pn[0].w, pn[1].x, pn[1].y, pn[1].z, pn[1].w};
+          if (use_p && grp < 7) { pn[0] = __ldg(prow32 + ((col + 16) >> 2) + 2 * mine); pn[1] = __ldg(prow32 + ((col + 16) >> 2) + 2 * mine + 1); }
           if ((grp & 3) == 0) wait_slot_free(slot);
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
           const int gcol = (col & 63) >> 3;
@@ -1221,7 +1259,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           for (int j = 0; j < 8; ++j) {
             // D_hi + D_lo in this order on both warps (the hi warp holds D_hi, the lo warp receives it)
             const float dsum = mine ? (pp[j] + __uint_as_float(keep[j])) : (__uint_as_float(keep[j]) + pp[j]);
-            r[j] = dsum * inv_scale + bbv[j] + hhv[j];
+            r[j] = dsum * inv_scale + bbv[j] + hhv[j] + ppv[j];
           }
           if (write_h) {
             scratch4[(size_t)((col >> 2) + 2 * mine) * kTileM + prow] = make_float4(r[0], r[1], r[2], r[3]);
@@ -1615,6 +1653,13 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
   a.raw_out = raw_out; a.d_out = w.d_out; a.dbg_sphere = dbg_sphere;
   a.skip_zero = (flags & SRF_FLAG_SKIP_ZERO_CHUNKS) ? 1 : 0;
   a.hidden_fp16 = (!split && (flags & SRF_FLAG_HIDDEN_FP16)) ? 1 : 0;
+  // pre-projected latent table: only for the pass the caller marks (the table belongs to ONE network) and only in the
+  // element type this mode reads (fp16 rows in fp16 mode, fp32 rows in split mode)
+  a.preproj = nullptr; a.pre_W1 = p.sphere_W + 1; a.pre_H1 = p.sphere_H + 1;
+  if ((flags & kTcFlagPreproj) && p.preproj && (p.preproj_fp16 != 0) == !split) {
+    a.preproj = reinterpret_cast<const unsigned char*>(p.preproj);
+    a.skip_zero = 0;
+  }
   a.debug_layer = debug_layer; a.debug_acc = debug_acc;
   a.zcache = reinterpret_cast<unsigned char*>(workspace) + (size_t)256 * tc::kTileM * kHidden * sizeof(float);
   if (const char* e = getenv("SRF_TC_ZCACHE")) { if (atoi(e) == 0) a.zcache = nullptr; }
