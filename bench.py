@@ -885,6 +885,35 @@ def run_render(args, rank, world, local_rank):
             v = quick(r, outs="all")
             v["note"] = "the reference's full 12-key dict incl. RaySOM (scenerf.py:456-469): +%d B/ray of output writes" % ((19 + 4 * cfg.S) * 4 - 16)
             variants["outputs=all"] = v
+        # pre-projected latent table (exact restructuring, SURVEY 7 hard part 3b): lin_z of the main network tabulated per
+        # sphere pixel once per image, 70.5 % of the per-point FLOPs never executed.  EXECUTED flops are reported apart
+        # from the algorithmic ones and never enter the roofline line above.
+        def table_variant(prec):
+            rp = mk_renderer(cfg, prec, preproject=True)
+            rp.set_profiling(True)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            rp.render_rays_batch(K, T, x_rgb, sampled_pixels=pix_dev[:256], outputs="minimal")
+            t1.record()
+            torch.cuda.synchronize()
+            v_ = quick(rp)
+            km = rp.last_mlp_ms()[1]
+            ems_ = time_loop(lambda: rp.render_rays_batch_host(K, T, x_rgb, pix_host, out_host), 3, 1, torch.cuda.synchronize)
+            exec_flop = float(R) * cfg.S * 2 * 1596416.0          # lin_in + 6 x 512x512 + lin_out per point
+            v_.update({"precision": prec, "kernel_ms": km, "e2e": {"value": R / (ems_ * 1e-3), "unit": "rays/s", "ms_per_frame": ems_},
+                       "first_call_ms_incl_pack_and_table": t0.elapsed_time(t1),
+                       "table_mb": rp._tab_buf.numel() / 1e6, "table_build_launches": rp.last_pack_launches,
+                       "executed_tflops": exec_flop / (km * 1e-3) / 1e12 * (4.0 if prec == "fp32tc" else 1.0),
+                       "algorithmic_tflops": flop_launch / (km * 1e-3) / 1e12,
+                       "note": "lin_z[b](z) of the main network read from a per-sphere-pixel table built once per image (srf_build_latent_table); "
+                               "executed MMA flops = 3.19 MFLOP/point (x4 issued in fp32tc) vs 10.81 algorithmic; value is ALGORITHMIC rays/s"})
+            del rp
+            torch.cuda.empty_cache()
+            return v_
+        if args.precision != "fp32" and not args.no_table_variant:
+            variants["latent_table (%s)" % args.precision] = table_variant(args.precision)
+            if args.precision != "fp16":
+                variants["latent_table (fp16)"] = table_variant("fp16")
         if args.precision != "fp32":
             n32 = min(R, 16384)
             r32 = mk_renderer(cfg, "fp32")
@@ -952,6 +981,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rays", type=int, default=0, help="diagnostics: use only the first N rays of the workload")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-table-variant", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / workload D / workload E measurements")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer (e2e) loop; 0 = same as --steps")
     args = ap.parse_args()

@@ -56,7 +56,10 @@ class RenderRaysFunction(torch.autograd.Function):
         gauss = dict(zip(PARAM_KEYS, pg))
         w_main, w_gauss = _weights_struct(main, 4), _weights_struct(gauss, 2)
         cfg = r._config(cam_K, T)
-        if r.save_activations:
+        # no input needs a gradient (validation under torch.no_grad(), the per-step depth-eval call of scenerf.py:189-200):
+        # nothing will read the activations -- do not store 24.4 KB per sample point
+        wants_grad = any(ctx.needs_input_grad)
+        if r.save_activations and wants_grad:
             cfg.flags |= _lib.FLAG_SAVE_ACTIVATIONS       # the backward reads the pre-activations instead of recomputing them
         if r.tf32_matmul:
             cfg.flags |= _lib.FLAG_SAVE_ACTIVATIONS | _lib.FLAG_TF32_MATMUL
@@ -127,7 +130,10 @@ class RenderRaysFunction(torch.autograd.Function):
                                                     ctx.ws.numel(), C.byref(gw_main), C.byref(gw_gauss), gp, _ptr(bws),
                                                     bws.numel(), _stream_ptr(r.device)))
             r.last_backward_launches = lib.srf_last_launch_count()
-        return (None, None, None, None, None, None, *g_maps, *g_main, *g_gauss)
+        # gradients only where autograd asked for them (a frozen encoder gets None for its five maps)
+        need = ctx.needs_input_grad[6:]
+        grads = [g if need[i] else None for i, g in enumerate(list(g_maps) + list(g_main) + list(g_gauss))]
+        return (None, None, None, None, None, None, *grads)
 
 
 class TrainableRenderer:

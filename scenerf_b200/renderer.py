@@ -86,7 +86,7 @@ class B200Renderer:
 
     def __init__(self, hp: dict, mlp_state, mlp_gaussian_state, device="cuda:0", precision: str = "fp16",
                  rng: str = "philox", skip_zero_chunks: bool = False, pyramid_fp16: bool = True,
-                 hidden_fp16: bool = True):
+                 hidden_fp16: bool = True, preproject: bool = False):
         if precision not in PRECISIONS:
             raise ValueError("precision must be one of %s" % list(PRECISIONS))
         if rng not in ("torch", "philox"):
@@ -101,6 +101,11 @@ class B200Renderer:
         self.skip_zero_chunks = skip_zero_chunks
         self.pyramid_fp16 = pyramid_fp16      # fp16 mode: store the packed pyramid as fp16 (half the gather bytes)
         self.hidden_fp16 = hidden_fp16        # fp16 mode: residual hidden state carried between blocks as fp16
+        # tensor-core modes: once per image, tabulate lin_z[b](z) of the main network per integer sphere pixel
+        # (srf_build_latent_table) and skip the three lin_z GEMM passes at render time -- exact in real arithmetic
+        self.preproject = bool(preproject) and precision in ("fp16", "fp32tc")
+        self._tab_buf = None
+        self.last_pack_launches = 0
         want_tc, want_split = precision == "fp16", precision == "fp32tc"
         self.mlp = _PackedMlp(mlp_state, 4, self.device, want_tc, want_split)
         self.mlp_gaussian = _PackedMlp(mlp_gaussian_state, 2, self.device, want_tc, want_split)
@@ -130,7 +135,7 @@ class B200Renderer:
         return cls(hp, model.mlp.state_dict(), model.mlp_gaussian.state_dict(), device=device, **kw)
 
     # ------------------------------------------------------------------------------------------------------------
-    def _pack_pyramid(self, x_rgb: Dict[str, torch.Tensor]):
+    def _pack_pyramid(self, x_rgb: Dict[str, torch.Tensor], cfg: Optional[Config] = None):
         ts = [x_rgb[k] for k in SCALE_KEYS]
         # The cached pack is reused only for the very same tensor OBJECTS, unmodified (same storage, same version
         # counter).  The renderer keeps references to the caller's tensors while the key is cached, so their storage
@@ -155,10 +160,38 @@ class B200Renderer:
         pyr = Pyramid()
         _lib.check(self.lib.srf_pack_pyramid(ptrs, Cs, Hs, Ws, fmt, _ptr(self._pyr_buf), nbytes, C.byref(pyr),
                                              _stream_ptr(self.device)))
+        if self.preproject:
+            self._build_latent_table(pyr, fmt, src, Cs, Hs, Ws, cfg)
         self._pyr, self._pyr_key = pyr, key
         self._pyr_held = ts          # the caller's own tensors (pins their storage while the key is cached)
         self._pyr_src = src          # fp32 contiguous copies, if any: alive until the async pack has certainly run
         return pyr
+
+    def _build_latent_table(self, pyr, fmt, src, Cs, Hs, Ws, cfg):
+        """srf_build_latent_table for the main network from an fp32 HWC pack of this image (a temporary one when the
+        render pack is fp16); the table pointer rides in the srf_pyramid struct."""
+        if cfg is None:
+            cfg = self._config(torch.eye(3), None)
+        dev = self.device
+        pyr32, keep = pyr, None
+        if fmt != _lib.PYR_FP32:
+            nb = self.lib.srf_pyramid_bytes(Cs, Hs, Ws, _lib.PYR_FP32)
+            keep = torch.empty(nb, dtype=torch.uint8, device=dev)
+            ptrs = (C.c_void_p * 5)(*[t.data_ptr() for t in src])
+            pyr32 = Pyramid()
+            _lib.check(self.lib.srf_pack_pyramid(ptrs, Cs, Hs, Ws, _lib.PYR_FP32, _ptr(keep), nb, C.byref(pyr32), _stream_ptr(dev)))
+        tfmt = _lib.PYR_FP16 if self.precision == "fp16" else _lib.PYR_FP32
+        nbytes = self.lib.srf_latent_table_bytes(C.byref(cfg), tfmt)
+        if self._tab_buf is None or self._tab_buf.numel() < nbytes:
+            self._tab_buf = None
+            self._tab_buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = torch.empty(self.lib.srf_latent_table_workspace_bytes(C.byref(pyr32)), dtype=torch.uint8, device=dev)
+        _lib.check(self.lib.srf_build_latent_table(C.byref(cfg), C.byref(pyr32), C.byref(self.mlp.struct), tfmt, _ptr(self._tab_buf),
+                                                   self._tab_buf.numel(), _ptr(ws), ws.numel(), _stream_ptr(dev)))
+        self.last_pack_launches = self.lib.srf_last_launch_count()
+        torch.cuda.current_stream(dev).synchronize()        # the temporaries (fp32 pack, GEMM workspace) die here
+        pyr.latent_table = self._tab_buf.data_ptr()
+        pyr.latent_table_format = tfmt
 
     def invalidate_pyramid(self):
         """Forget the cached feature-pyramid pack (call after writing into x_rgb through .data / raw pointers)."""
@@ -233,7 +266,7 @@ class B200Renderer:
             raise ValueError("sampled_pixels must be (R,2), got %s" % (tuple(pix.shape),))
         R = int(pix.shape[0])
         cfg = self._config(cam_K, T_source2infer)
-        pyr = self._pack_pyramid(x_rgb)
+        pyr = self._pack_pyramid(x_rgb, cfg)
         G, S = cfg.n_gaussians, cfg.n_pts_uni + cfg.n_gaussians * cfg.n_pts_per_gaussian
         keys = DICT_KEYS if outputs == "all" else MINIMAL_KEYS
         shapes = dict(depth=(R,), color=(R, 3), gaussian_means=(R, G), gaussian_stds=(R, G), weights_at_depth=(R,),
@@ -288,7 +321,7 @@ class B200Renderer:
         vd = viewdir.detach().to(device=self.device, dtype=torch.float32).contiguous()
         n_cols, n_per = saved[0], saved[1]
         cfg = self._config(cam_K, None)
-        pyr = self._pack_pyramid(x_rgb)
+        pyr = self._pack_pyramid(x_rgb, cfg)
         n = n_cols * n_per
         d_out = net.struct.d_out
         raw = torch.empty((n, d_out), dtype=torch.float32, device=self.device)
@@ -320,7 +353,7 @@ class B200Renderer:
             raise ValueError("sampled_pixels_host must be a contiguous float32 CPU tensor")
         R = int(pix.shape[0])
         cfg = self._config(cam_K, T_source2infer)
-        pyr = self._pack_pyramid(x_rgb)
+        pyr = self._pack_pyramid(x_rgb, cfg)
         if out_host is None:
             out_host = {"depth": torch.empty((R,), dtype=torch.float32).pin_memory(),
                         "color": torch.empty((R, 3), dtype=torch.float32).pin_memory()}
@@ -355,7 +388,7 @@ class B200Renderer:
         vd = viewdir.detach().to(device=self.device, dtype=torch.float32).contiguous()
         n_cols, n_per = pts.shape[0], pts.shape[1]
         cfg = self._config(cam_K, None)
-        pyr = self._pack_pyramid(x_rgb)
+        pyr = self._pack_pyramid(x_rgb, cfg)
         n = n_cols * n_per
         tile = 64 if self.precision == "fp32tc" else 128
         acc = torch.zeros(((n + tile - 1) // tile * 128, 512), dtype=torch.float32, device=self.device)

@@ -23,6 +23,11 @@ def get_sphere_feature(x: torch.Tensor, pix: torch.Tensor, pix_sphere: torch.Ten
     """x (B,C,h,w) float32 CUDA; pix (n,2) float32; pix_sphere (n,2) int64 -> (B,C,out_H,out_W) (or (B,out_H,out_W,C))."""
     if x.device.type != "cuda":
         raise RuntimeError("scenerf_b200.sphere_feature is the device path (no CPU fallback)")
+    if x.requires_grad and torch.is_grad_enabled():
+        # the reference method is differentiable through F.grid_sample into the decoder; this kernel has no backward --
+        # used inside a training graph it would silently cut every gradient to the U-Net
+        raise RuntimeError("scenerf_b200.get_sphere_feature is inference-only (no backward): call it under torch.no_grad() "
+                           "or keep the reference's DecoderSphere.get_sphere_feature for training")
     lib = _lib.load()
     x = x.detach().to(torch.float32).contiguous()
     pix = pix.detach().to(device=x.device, dtype=torch.float32).contiguous()

@@ -61,9 +61,9 @@ def test_full_size_vs_reference_golden(name):
         _compare_with_golden(name, cfg, g, prec, pyr)
 
 
-def _compare_with_golden(name, cfg, g, prec, pyr_np):
+def _compare_with_golden(name, cfg, g, prec, pyr_np, **renderer_kw):
     import torch
-    r = make_renderer(cfg, prec)
+    r = make_renderer(cfg, prec, **renderer_kw)
     x_rgb = {k: torch.from_numpy(v).to("cuda:0") for k, v in pyr_np.items()}
     out = _np(r.render_rays_batch(torch.from_numpy(cfg.K), torch.from_numpy(cfg.T), x_rgb,
                                   sampled_pixels=torch.from_numpy(g["pixels"]), ray_batch_size=g["pixels"].shape[0],
