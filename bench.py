@@ -744,7 +744,7 @@ def run_render(args, rank, world, local_rank):
     def mk_renderer(c, precision=None, **kw):
         return B200Renderer(hp_from_cfg(c), to_t(pm), to_t(pg), device=dev, precision=precision or args.precision, rng="philox", **kw)
 
-    r = mk_renderer(cfg, skip_zero_chunks=bool(args.skip_zero_chunks))
+    r = mk_renderer(cfg, skip_zero_chunks=bool(args.skip_zero_chunks), preproject=bool(args.latent_table))
     gen = torch.Generator(device=dev)
     gen.manual_seed(5)                                 # the same source-frame features on every rank (novel poses differ)
     x_rgb = {k: torch.randn((c, h, w), generator=gen, device=dev) * 0.5
@@ -952,7 +952,7 @@ def run_render(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": PREC_DTYPE[args.precision], "data": "synthetic",
             "config": {"workload": desc, "rays_per_gpu": R, "samples_per_ray": cfg.S, "parallelism": "frame-per-GPU x%d (one pose of the source frame per GPU + all-gather of depth+rgb)" % world,
                        "precision": args.precision + ": " + PREC_DESC[args.precision],
-                       "skip_zero_chunks": bool(args.skip_zero_chunks), "outputs": "depth+color" if outputs == "minimal" else "the reference's 12-key dict",
+                       "skip_zero_chunks": bool(args.skip_zero_chunks), "latent_table": bool(args.latent_table), "outputs": "depth+color" if outputs == "minimal" else "the reference's 12-key dict",
                        "l2": "inputs larger than L2: %.0f MB %s pyramid + %d MB weights + 1.9 GB of per-step intermediates (points, raw MLP output); no flush needed"
                              % (pyr_mb, fmt, 44 if args.precision == "fp32tc" else 22)},
             "clocks": clocks,
@@ -982,6 +982,7 @@ def main():
     ap.add_argument("--rays", type=int, default=0, help="diagnostics: use only the first N rays of the workload")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-table-variant", action="store_true")
+    ap.add_argument("--latent-table", type=int, default=0, help="1: the timed renderer uses the pre-projected latent table (diagnostics / profiling)")
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / workload D / workload E measurements")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer (e2e) loop; 0 = same as --steps")
     args = ap.parse_args()

@@ -80,6 +80,7 @@ typedef struct srf_pyramid {
   int C[SRF_NUM_SCALES], H[SRF_NUM_SCALES], W[SRF_NUM_SCALES];
   int format;                        /* srf_pyramid_format */
   const void* latent_table;          /* optional: srf_build_latent_table() output for the MAIN network (`mlp`), else NULL */
+  const void* latent_table_gauss;    /* optional: the same for `mlp_gaussian` (its own lin_z weights), else NULL */
   int latent_table_format;           /* srf_pyramid_format of the table rows: FP16 is used by SRF_PREC_FP16_TC, FP32 by SRF_PREC_FP32_TC */
 } srf_pyramid;
 
@@ -166,13 +167,14 @@ int srf_pack_weights_tc_split(const srf_mlp_weights* w, void* dst_dev, size_t ds
  * coordinates to integers (spherical_mapping.py:115), so the 2480-channel latent of a sample point -- and therefore
  * lin_z[b](z) of resnetfc.py:148-150 -- is a function of the integer sphere pixel only.  The table holds
  * lin_z[b].weight . z(pixel) (3 x 512 values) for every pixel that can have a valid bilinear tap (+ one zero row); with
- * `pyr->latent_table` set, the tensor-core modes skip the three lin_z GEMM passes of the MAIN network (70.5 % of the
- * per-point FLOPs) and add the table row in the epilogue.  Exact in real arithmetic; rounding differs from the dense
+ * `pyr->latent_table` (`latent_table_gauss`) set, the tensor-core modes skip the three lin_z GEMM passes of the main
+ * (gaussian-proposal) network -- 70.5 % of the per-point FLOPs -- and add the table row in the epilogue.  A table
+ * belongs to ONE network: build it with that network's weights.  Exact in real arithmetic; rounding differs from the dense
  * path at float32 round-off (fp32 table) / fp16 round-off (fp16 table).  pyr must be an SRF_PYR_FP32 pack.
  * Sizes: table (sphere_W+1)*(sphere_H+1)*1536 values (config B: 1.4 GB fp16 / 2.8 GB fp32); workspace 2 KB per texel. */
 size_t srf_latent_table_bytes(const srf_config* cfg, int format);
 size_t srf_latent_table_workspace_bytes(const srf_pyramid* pyr);
-int srf_build_latent_table(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w_main, int format,
+int srf_build_latent_table(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w, int format,
                            void* table_dev, size_t table_bytes, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* --- the hot path ----------------------------------------------------------------------------------------- */
@@ -264,6 +266,26 @@ void srf_sphere_feature_dims(int out_img_W, int out_img_H, int scale, int* out_W
 int srf_sphere_feature(const float* x_chw_dev, int C, int h, int w, const float* pix_dev, const long long* pix_sphere_dev,
                        int n_pixels, int scale, int out_img_W, int out_img_H, float* out_dev, int out_hwc,
                        void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* --- next row (producer side): the convolutional tail of the spherical decoder, channels-last ------------------------------------
+ * `UpSampleBN` / `BasicBlock` of scenerf/models/unet2d_sphere.py:9-57 as applied by `DecoderSphere.forward` (:167-206), whose five
+ * outputs are the x_rgb pyramid.  All maps are [H][W][C] float32 with a channel stride `ld` that is a multiple of 4 (padding
+ * channels hold zeros); BatchNorm is applied in eval mode, folded by the caller into per-channel scale / shift.
+ *   srf_upsample_concat_hwc : F.interpolate(x, size=(H,W), bilinear, align_corners=True) of the coarser map x (h,w,Cx) concatenated
+ *                             in front of skip (H,W,Cs) -> out (H,W,ld_out), channels [Cx+Cs, ld_out) zeroed      (unet2d_sphere.py:47-56)
+ *   srf_conv3x3_hwc         : y = LeakyReLU_slope( conv3x3(in; dilation = padding = dil) * scale + shift (+ residual) ); slope 1 = none.
+ *                             w9_dev: weights repacked [9][Cout][ld_in] (tap = ky*3 + kx; Conv2d.weight[co][ci][ky][kx]), zero for
+ *                             padded ci.  Writes out32_dev (H,W,ld32) float32 and/or out16_dev (H,W,ld16) IEEE half -- with
+ *                             ld = Cout these ARE the buffers srf_pyramid.hwc[] points to (no CHW->HWC pass).  tcgen05 kind::tf32
+ *                             implicit GEMM, operands read as fp32 with a 10-bit mantissa (cuDNN's default allow_tf32 regime).  The
+ *                             tensor core truncates; feed it tensors already rounded to the nearest tf32 value (w9 rounded by the
+ *                             caller; round_out != 0 stores out32 rounded because it feeds another convolution; the concat kernel
+ *                             always rounds) and the truncation is exact -- 6.7x less error through the 35 chained convolutions. */
+int srf_upsample_concat_hwc(const float* x_dev, int h, int w, int Cx, int ld_x, const float* skip_dev, int Cs, int ld_skip, int H, int W,
+                            float* out_dev, int ld_out, void* stream);
+int srf_conv3x3_hwc(const float* in_dev, int H, int W, int ld_in, const float* w9_dev, int Cout, int dil, const float* scale_dev,
+                    const float* shift_dev, const float* residual_dev, int ld_res, float slope, int round_out, float* out32_dev, int ld32,
+                    void* out16_dev, int ld16, void* stream);
 
 /* Diagnostic: one GEMM of the training path, C[M x N] = epilogue(A[M x K] * B[N x K]^T) with float32 device operands.
  * use_tf32 != 0 runs the tcgen05 kind::tf32 kernel (csrc/gemm_tf32.cu), 0 the float32 SIMT kernel (csrc/gemm.cu).

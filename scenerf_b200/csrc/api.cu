@@ -132,6 +132,7 @@ srf::DevParams make_params(const srf_config* cfg, const srf_pyramid* pyr) {
     p.ch_off[SRF_NUM_SCALES] = off;
     p.d_latent = off;
     p.preproj = pyr->latent_table;
+    p.preproj_gauss = pyr->latent_table_gauss;
     p.preproj_fp16 = pyr->latent_table_format == SRF_PYR_FP16;
   }
   return p;
@@ -166,8 +167,11 @@ int run_mlp(const srf::DevParams& p, int precision, int flags, const srf_mlp_wei
   else {
     int f = flags & ~(srf::kTcFlagSplit | srf::kTcFlagPreproj);
     if (precision == SRF_PREC_FP32_TC) f |= srf::kTcFlagSplit;
-    if (w.d_out == 4) f |= srf::kTcFlagPreproj;               // the latent table belongs to the main network
-    l = srf::run_point_mlp_tc(p, w, pts, viewdir, n, n_per, raw, dbg, f, ws, ws_bytes, st);
+    // a latent table belongs to one network: the main pass (d_out 4) reads latent_table, the proposal pass latent_table_gauss
+    srf::DevParams pp = p;
+    pp.preproj = (w.d_out == 4) ? p.preproj : p.preproj_gauss;
+    if (pp.preproj) f |= srf::kTcFlagPreproj;
+    l = srf::run_point_mlp_tc(pp, w, pts, viewdir, n, n_per, raw, dbg, f, ws, ws_bytes, st);
   }
   if (l < 0) return fail(SRF_E_WORKSPACE, "point-MLP workspace too small (%zu bytes)", ws_bytes);
   prof_record(2 * pass + 1, st);
@@ -263,6 +267,7 @@ int srf_pack_pyramid(const float* const* chw_dev, const int* C, const int* H, co
   const size_t esz = format == SRF_PYR_FP16 ? 2 : 4;
   out->format = format;
   out->latent_table = nullptr;
+  out->latent_table_gauss = nullptr;
   out->latent_table_format = 0;
   unsigned char* d = reinterpret_cast<unsigned char*>(dst_dev);
   for (int s = 0; s < SRF_NUM_SCALES; ++s) {
@@ -318,6 +323,7 @@ int srf_build_latent_table(const srf_config* cfg, const srf_pyramid* pyr, const 
                 srf_latent_table_bytes(cfg, format), srf_latent_table_workspace_bytes(pyr));
   srf_pyramid plain = *pyr;
   plain.latent_table = nullptr;
+  plain.latent_table_gauss = nullptr;
   const srf::DevParams p = make_params(cfg, &plain);
   const int l = srf::run_preproject(p, *w_main, format == SRF_PYR_FP16, table_dev, table_bytes, workspace_dev, workspace_bytes,
                                     (cudaStream_t)stream);
@@ -627,6 +633,35 @@ int srf_sphere_feature(const float* x_chw_dev, int C, int h, int w, const float*
                              reinterpret_cast<int*>(workspace_dev), out_dev, out_hwc, (cudaStream_t)stream);
   g_launches = 3;
   return check_cuda("srf_sphere_feature");
+}
+
+int srf_upsample_concat_hwc(const float* x_dev, int h, int w, int Cx, int ld_x, const float* skip_dev, int Cs, int ld_skip, int H, int W,
+                            float* out_dev, int ld_out, void* stream) {
+  if (!x_dev || !skip_dev || !out_dev || h < 1 || w < 1 || H < 1 || W < 1 || Cx < 1 || Cs < 0 || ld_x < Cx || ld_skip < Cs ||
+      ld_out < Cx + Cs)
+    return fail(SRF_E_INVALID, "srf_upsample_concat_hwc: bad argument (x %dx%dx%d/%d, skip %dx%dx%d/%d, out ld %d)", h, w, Cx, ld_x, H, W, Cs,
+                ld_skip, ld_out);
+  srf::launch_upsample_concat(x_dev, h, w, Cx, ld_x, skip_dev, Cs, ld_skip, H, W, out_dev, ld_out, (cudaStream_t)stream);
+  g_launches = 1;
+  return check_cuda("srf_upsample_concat_hwc");
+}
+
+int srf_conv3x3_hwc(const float* in_dev, int H, int W, int ld_in, const float* w9_dev, int Cout, int dil, const float* scale_dev,
+                    const float* shift_dev, const float* residual_dev, int ld_res, float slope, int round_out, float* out32_dev, int ld32,
+                    void* out16_dev, int ld16, void* stream) {
+  if (!in_dev || !w9_dev || !scale_dev || !shift_dev || (!out32_dev && !out16_dev))
+    return fail(SRF_E_INVALID, "srf_conv3x3_hwc: NULL argument");
+  if ((out32_dev && ld32 < Cout) || (out16_dev && ld16 < Cout) || (residual_dev && ld_res < Cout))
+    return fail(SRF_E_INVALID, "srf_conv3x3_hwc: a channel stride is smaller than Cout=%d", Cout);
+  const int rc = srf::launch_conv3x3_tf32(in_dev, H, W, ld_in, w9_dev, Cout, dil, scale_dev, shift_dev, residual_dev, ld_res, slope, round_out,
+                                          out32_dev, ld32, out16_dev, ld16, (cudaStream_t)stream);
+  if (rc == -2) return fail(SRF_E_UNSUPPORTED, "srf_conv3x3_hwc: cuTensorMapEncodeTiled is not available");
+  if (rc) return fail(SRF_E_INVALID, "srf_conv3x3_hwc: shape or alignment not supported (H=%d W=%d ld_in=%d Cout=%d dil=%d; strides must be "
+                                     "multiples of 4 floats, pointers 16-byte aligned)", H, W, ld_in, Cout, dil);
+  g_launches = 1;
+  const int e = check_cuda("srf_conv3x3_hwc");
+  if (e) return fail(SRF_E_CUDA, "%s (conv watchdog flag 0x%x)", srf_last_error(), srf::conv_watchdog_flag());
+  return e;
 }
 
 int srf_debug_tc_layer(const srf_config* cfg, const srf_pyramid* pyr, const srf_mlp_weights* w,

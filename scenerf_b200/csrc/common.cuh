@@ -38,7 +38,8 @@ struct DevParams {
   float halfW[kScales], halfH[kScales];   // float(W_t/2), float(H_t/2): ATen CPU unnormalise scaling factor
   int d_latent;                       // sum C
   uint64_t seed;
-  const void* preproj;                // srf_pyramid.latent_table (pre-projected lin_z of the main network) or null
+  const void* preproj;                // srf_pyramid.latent_table (pre-projected lin_z of the network of THIS pass) or null
+  const void* preproj_gauss;          // srf_pyramid.latent_table_gauss (api.cu moves it into `preproj` for the proposal pass)
   int preproj_fp16;
   uint32_t ray0;                      // srf_config.ray_offset: Philox counter of ray r is (seed, ray0 + r, sample)
 };

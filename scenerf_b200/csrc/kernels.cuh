@@ -97,6 +97,15 @@ int run_point_mlp_tc(const DevParams& p, const srf_mlp_weights& w, const float* 
                      int n_per, float* raw_out, int32_t* dbg_sphere, int flags, void* workspace, size_t ws_bytes,
                      cudaStream_t st);
 
+// conv_tf32.cu : the spherical decoder's 3x3 (dilated) convolutions as a tcgen05 kind::tf32 implicit GEMM on channels-last maps
+//   (unet2d_sphere.py:9-57) + the UpSampleBN front end (bilinear align_corners=True upsample of the coarser map, concat with the skip map)
+int launch_conv3x3_tf32(const float* in, int H, int W, int Cin, const float* w9, int Cout, int dil, const float* scale, const float* shift,
+                        const float* residual, int ld_res, float slope, int round_out, float* out32, int ld32, void* out16, int ld16,
+                        cudaStream_t st);
+void launch_upsample_concat(const float* x, int h, int w, int Cx, int ldx, const float* skip, int Cs, int lds, int H, int W, float* out, int ld,
+                            cudaStream_t st);
+int conv_watchdog_flag();
+
 // preproj.cu : pre-projected latent table  table[(sy,sx)][block][512] = lin_z[block].weight . z(sphere pixel)  (see file header)
 size_t preproj_rows(int sphere_W, int sphere_H);
 size_t preproj_table_bytes(int sphere_W, int sphere_H, int fp16);

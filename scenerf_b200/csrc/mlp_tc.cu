@@ -1079,10 +1079,6 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       //   16-column groups; TMEM load, scratch and bias of group g+1 are in flight while group g is processed.
       auto epilogue_half = [&](int part, int bias_idx, bool use_h, bool write_h) {
         lap(1);
-        mbar_wait(half_full(part), half_par[part], a.error_flag);
-        half_par[part] ^= 1;
-        tc_fence_after();
-        lap(2);
         const float4* b4 = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden);
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const int col0 = part * 256 + sub * 128;
@@ -1112,16 +1108,23 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         const uint4* prow16 = reinterpret_cast<const uint4*>(pre_row + (size_t)bias_idx * kHidden * 2);
         uint4 pn[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
         if (use_p) { pn[0] = __ldg(prow16 + (col0 >> 3)); pn[1] = __ldg(prow16 + (col0 >> 3) + 1); }
-        tmem_ld16(trow + (uint32_t)col0, vn);
+        // the operands that do not depend on the accumulator (hidden state, table row) are requested BEFORE waiting for it:
+        // their L2 latency runs under the wait
         load_h(hx, col0);
         load_h(hy, col0 + 16);
+        mbar_wait(half_full(part), half_par[part], a.error_flag);
+        half_par[part] ^= 1;
+        tc_fence_after();
+        lap(2);
+        tmem_ld16(trow + (uint32_t)col0, vn);
         auto process = [&](int grp, float4 (&hbuf)[4]) {
           const int col = col0 + grp * 16;
           float4 bb[4], hh[4];
           const uint4 pc0 = pn[0], pc1 = pn[1];
           if (use_p && grp < 7) { pn[0] = __ldg(prow16 + ((col + 16) >> 3)); pn[1] = __ldg(prow16 + ((col + 16) >> 3) + 1); }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) bb[j] = __ldg(b4 + (col >> 2) + j);   // 16 KB bias header: L1-resident broadcast
+          for (int j = 0; j < 4; ++j)     // 16 KB bias header: L1-resident broadcast; a latent-table row already contains c_b
+            bb[j] = use_p ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b4 + (col >> 2) + j);
           tmem_ld_wait();
           uint32_t v[16];
 #pragma unroll
@@ -1199,10 +1202,6 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       //   (D_hi + D_lo) * 2^-s + bias (+ h), ReLU, hi/lo split, two 16-byte A-tile stores.
       auto epilogue_half_split = [&](int part, int bias_idx, bool use_h, bool write_h) {
         lap(1);
-        mbar_wait(half_full(part), half_par[part], a.error_flag);
-        half_par[part] ^= 1;
-        tc_fence_after();
-        lap(2);
         const int mine = (q4 < 2) ? 0 : 1;                      // 0: hi warp, finishes columns 0-7 of a group; 1: lo warp, 8-15
         const int pair_bar = 2 + (q4 & 1) * 2 + sub;            // named barriers 2..5: one per (hi, lo) warp pair
         const int prow = (q4 & 1) * 32 + lane;                  // point row (0..63) of this lane
@@ -1221,8 +1220,12 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         const float4* prow32 = reinterpret_cast<const float4*>(pre_row + (size_t)bias_idx * kHidden * 4);
         float4 pn[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
         if (use_p) { pn[0] = __ldg(prow32 + (col0 >> 2) + 2 * mine); pn[1] = __ldg(prow32 + (col0 >> 2) + 2 * mine + 1); }
+        load_h(hn, col0);                                       // accumulator-independent operands first: latency under the wait
+        mbar_wait(half_full(part), half_par[part], a.error_flag);
+        half_par[part] ^= 1;
+        tc_fence_after();
+        lap(2);
         tmem_ld16(trow + (uint32_t)col0, vn);
-        load_h(hn, col0);
         for (int grp = 0; grp < 8; ++grp) {
           const int col = col0 + grp * 16;
           const int slot = col >> 6;
@@ -1236,7 +1239,10 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           const uint32_t peer0 = slot_addr + sw128_offset(prow, gcol + 1 - mine), peer1 = slot_addr + sw128_offset(prow + kPts, gcol + 1 - mine);
           float4 bb[2], hh[2];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) { bb[j] = __ldg(b4 + (col >> 2) + 2 * mine + j); hh[j] = hn[j]; }
+          for (int j = 0; j < 2; ++j) {     // a latent-table row already contains the cumulative bias c_b
+            bb[j] = use_p ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b4 + (col >> 2) + 2 * mine + j);
+            hh[j] = hn[j];
+          }
           tmem_ld_wait();
           uint32_t v[16];
 #pragma unroll
@@ -1306,7 +1312,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
 
       // ---------------- the tile program (worker side; MMA side: walk_tile) -------------------------------------
       lap(0);
-      gather_pass(0);                                             // lin_z0
+      const bool do_gather = a.preproj == nullptr;                // latent table: no lin_z chunk exists, nothing to gather or sync
+      if (do_gather) gather_pass(0);                              // lin_z0
       if (a.debug_layer == 1) { dump_acc(true); continue; }
       bool stop = false;
       for (int b = 0; b < SRF_NUM_BLOCKS; ++b) {
@@ -1316,7 +1323,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         epilogue(0, 3 + b, false, false);                         // E2a -> A chunks 0-3 of fc_1 (overlaps fc_0 S4)
         epilogue(1, 3 + b, false, false);                         // E2b (overlaps fc_1 S1)
         if (b < SRF_NUM_BLOCKS - 1) {
-          gather_pass(b + 1);                                     // lin_z(b+1), consumed between fc_1 S2 and S3
+          if (do_gather) gather_pass(b + 1);                      // lin_z(b+1), consumed between fc_1 S2 and S3
           if (a.debug_layer == 4 + 3 * b) { dump_acc(true); stop = true; break; }
         } else {
           // last block: nothing to gather while fc_1 runs -> prepare the next tile's geometry / chunk mask now

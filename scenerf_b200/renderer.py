@@ -135,7 +135,9 @@ class B200Renderer:
         return cls(hp, model.mlp.state_dict(), model.mlp_gaussian.state_dict(), device=device, **kw)
 
     # ------------------------------------------------------------------------------------------------------------
-    def _pack_pyramid(self, x_rgb: Dict[str, torch.Tensor], cfg: Optional[Config] = None):
+    def _pack_pyramid(self, x_rgb, cfg: Optional[Config] = None):
+        if hasattr(x_rgb, "struct") and hasattr(x_rgb, "buf32"):
+            return self._adopt_packed(x_rgb, cfg)
         ts = [x_rgb[k] for k in SCALE_KEYS]
         # The cached pack is reused only for the very same tensor OBJECTS, unmodified (same storage, same version
         # counter).  The renderer keeps references to the caller's tensors while the key is cached, so their storage
@@ -167,13 +169,32 @@ class B200Renderer:
         self._pyr_src = src          # fp32 contiguous copies, if any: alive until the async pack has certainly run
         return pyr
 
-    def _build_latent_table(self, pyr, fmt, src, Cs, Hs, Ws, cfg):
+    def _adopt_packed(self, packed, cfg):
+        """x_rgb is a scenerf_b200.decoder.PackedPyramid: the producer already wrote the channels-last layout (fp32 and,
+        optionally, fp16) -- no srf_pack_pyramid pass."""
+        fmt = _lib.PYR_FP16 if (self.precision == "fp16" and self.pyramid_fp16 and packed.buf16 is not None) else _lib.PYR_FP32
+        key = ("packed", id(packed), packed.version, fmt)
+        if key == self._pyr_key and self._pyr_held is packed:
+            return self._pyr
+        pyr = packed.struct(fmt)
+        if self.preproject:
+            p32 = packed.struct(_lib.PYR_FP32)
+            Cs = (C.c_int * 5)(*[s[0] for s in packed.shapes])
+            Hs = (C.c_int * 5)(*[s[1] for s in packed.shapes])
+            Ws = (C.c_int * 5)(*[s[2] for s in packed.shapes])
+            self._build_latent_table(pyr, _lib.PYR_FP32, None, Cs, Hs, Ws, cfg, pyr32=p32)
+        self._pyr, self._pyr_key, self._pyr_held, self._pyr_src = pyr, key, packed, None
+        return pyr
+
+    def _build_latent_table(self, pyr, fmt, src, Cs, Hs, Ws, cfg, pyr32=None):
         """srf_build_latent_table for the main network from an fp32 HWC pack of this image (a temporary one when the
         render pack is fp16); the table pointer rides in the srf_pyramid struct."""
         if cfg is None:
             cfg = self._config(torch.eye(3), None)
         dev = self.device
-        pyr32, keep = pyr, None
+        keep = None
+        if pyr32 is None:
+            pyr32 = pyr
         if fmt != _lib.PYR_FP32:
             nb = self.lib.srf_pyramid_bytes(Cs, Hs, Ws, _lib.PYR_FP32)
             keep = torch.empty(nb, dtype=torch.uint8, device=dev)
@@ -182,15 +203,19 @@ class B200Renderer:
             _lib.check(self.lib.srf_pack_pyramid(ptrs, Cs, Hs, Ws, _lib.PYR_FP32, _ptr(keep), nb, C.byref(pyr32), _stream_ptr(dev)))
         tfmt = _lib.PYR_FP16 if self.precision == "fp16" else _lib.PYR_FP32
         nbytes = self.lib.srf_latent_table_bytes(C.byref(cfg), tfmt)
-        if self._tab_buf is None or self._tab_buf.numel() < nbytes:
+        if self._tab_buf is None or self._tab_buf.numel() < 2 * nbytes:
             self._tab_buf = None
-            self._tab_buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._tab_buf = torch.empty(2 * nbytes, dtype=torch.uint8, device=dev)      # main network, then mlp_gaussian
         ws = torch.empty(self.lib.srf_latent_table_workspace_bytes(C.byref(pyr32)), dtype=torch.uint8, device=dev)
-        _lib.check(self.lib.srf_build_latent_table(C.byref(cfg), C.byref(pyr32), C.byref(self.mlp.struct), tfmt, _ptr(self._tab_buf),
-                                                   self._tab_buf.numel(), _ptr(ws), ws.numel(), _stream_ptr(dev)))
-        self.last_pack_launches = self.lib.srf_last_launch_count()
+        self.last_pack_launches = 0
+        for i, net in enumerate((self.mlp, self.mlp_gaussian)):
+            tab = self._tab_buf[i * nbytes:(i + 1) * nbytes]
+            _lib.check(self.lib.srf_build_latent_table(C.byref(cfg), C.byref(pyr32), C.byref(net.struct), tfmt, _ptr(tab),
+                                                       nbytes, _ptr(ws), ws.numel(), _stream_ptr(dev)))
+            self.last_pack_launches += self.lib.srf_last_launch_count()
         torch.cuda.current_stream(dev).synchronize()        # the temporaries (fp32 pack, GEMM workspace) die here
         pyr.latent_table = self._tab_buf.data_ptr()
+        pyr.latent_table_gauss = self._tab_buf.data_ptr() + nbytes
         pyr.latent_table_format = tfmt
 
     def invalidate_pyramid(self):

@@ -214,3 +214,47 @@ def make_model_params(cfg: "SceneConfig", seed: int = 11):
     main = make_mlp_params(seed, 4, out_scale=0.1, out_bias=[0.0, -2.0, 0.9, dens_bias])
     gauss = make_mlp_params(seed + 1, 2, out_scale=0.1, out_bias=[3.3, 2.6])
     return main, gauss
+
+
+# ---- spherical decoder (producer of the pyramid): scenerf/models/unet2d_sphere.py:60-135 ------------------------------------------
+DECODER_SKIP_CHANNELS = {16: 224, 8: 80, 4: 48, 2: 32, 1: 3}       # EfficientNet block widths the decoder concatenates (unet2d_sphere.py:91-105)
+
+
+def decoder_level_channels(num_features: int):
+    """up-level -> (Cin of its first conv, Cout), as DecoderSphere.__init__ wires them (unet2d_sphere.py:84-135)."""
+    f = int(num_features)
+    out = {16: f // 2, 8: f // 4, 4: f // 8, 2: f // 16, 1: f // 32}
+    prev = {16: f, 8: out[16], 4: out[8], 2: out[4], 1: out[2]}
+    return {s: (prev[s] + DECODER_SKIP_CHANNELS[s], out[s]) for s in (16, 8, 4, 2, 1)}
+
+
+def make_decoder_params(num_features: int, bottleneck_features: int, seed: int = 21):
+    """Deterministic DecoderSphere parameters + BatchNorm running statistics (state_dict names of unet2d_sphere.py), for the
+    modules `forward` uses: conv2 and up16/up8/up4/up2/up1 (`_net.0` conv, `_net.1-3` BasicBlocks)."""
+    p = {}
+    k = [0]
+
+    def nxt():
+        k[0] += 1
+        return seed * 1000 + k[0]
+
+    def conv(name, cout, cin, ks):
+        n = cout * cin * ks * ks
+        p[name + ".weight"] = (hash_normalish(nxt(), n) * np.float32(math.sqrt(2.0 / (cin * ks * ks)))).reshape(cout, cin, ks, ks).astype(np.float32)
+        p[name + ".bias"] = (hash_uniform(nxt(), cout) * np.float32(0.1)).astype(np.float32)
+
+    def bn(name, c):
+        p[name + ".weight"] = (np.float32(1.0) + hash_uniform(nxt(), c) * np.float32(0.3)).astype(np.float32)
+        p[name + ".bias"] = (hash_uniform(nxt(), c) * np.float32(0.2)).astype(np.float32)
+        p[name + ".running_mean"] = (hash_uniform(nxt(), c) * np.float32(0.2)).astype(np.float32)
+        p[name + ".running_var"] = (np.float32(1.0) + hash_uniform(nxt(), c) * np.float32(0.4)).astype(np.float32)
+
+    conv("conv2", int(num_features), int(bottleneck_features), 1)
+    for s, (cin, cout) in decoder_level_channels(num_features).items():
+        pre = "up%d._net." % s
+        conv(pre + "0", cout, cin, 3)
+        for blk in (1, 2, 3):
+            for cb in (1, 2):
+                conv(pre + "%d.conv_block%d.0" % (blk, cb), cout, cout, 3)
+                bn(pre + "%d.conv_block%d.1" % (blk, cb), cout)
+    return p

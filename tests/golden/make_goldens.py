@@ -455,6 +455,51 @@ def sphere_feature():
     return out
 
 
+DECODER_CASE = dict(num_features=128, bottleneck=48, W=128, H=64, oW=150, oH=46, seed=21)
+
+
+def decoder_inputs(c=DECODER_CASE):
+    """Deterministic encoder maps (the six `features[...]` DecoderSphere.forward reads, unet2d_sphere.py:168-175) + camera."""
+    chans = {1: 3, 2: 32, 4: 48, 8: 80, 16: 224, 32: c["bottleneck"]}
+    feats = {}
+    for s, ch in chans.items():
+        h, w = -(-c["H"] // s), -(-c["W"] // s)
+        feats[s] = synth.hash_normalish(500 + s, ch * h * w).reshape(ch, h, w).astype(np.float32)
+    K = synth.KITTI_K.copy()
+    K[:2] /= 9.5
+    return feats, K
+
+
+@case
+def decoder_sphere():
+    """DecoderSphere.forward (unet2d_sphere.py:167-206) in eval mode on deterministic weights: conv2, six get_sphere_feature
+    resamplings, five UpSampleBN stacks -> the five maps of the x_rgb pyramid."""
+    _install_shims()
+    from scenerf.models.unet2d_sphere import DecoderSphere
+    from scenerf.models.spherical_mapping import SphericalMapping
+    torch.set_num_threads(1)
+    c = DECODER_CASE
+    feats, K = decoder_inputs()
+    cfg = synth.config_A(name="dec", sphere_W=c["oW"], sphere_H=c["oH"])
+    v0, v1, h0, h1 = cfg.angles()
+    sm = SphericalMapping(v_angle_max=v1, v_angle_min=v0, h_angle_max=h1, h_angle_min=h0, img_W=c["W"], img_H=c["H"],
+                          out_img_W=c["oW"], out_img_H=c["oH"])
+    pix, pix_sphere, _ = sm.from_pixels(inv_K=torch.inverse(torch.from_numpy(K)))
+    dec = DecoderSphere(num_features=c["num_features"], bottleneck_features=c["bottleneck"], out_feature=16, out_img_W=c["oW"],
+                        out_img_H=c["oH"]).eval()
+    params = synth.make_decoder_params(c["num_features"], c["bottleneck"], c["seed"])
+    missing, unexpected = dec.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=False)
+    assert not unexpected and all(m.startswith("resize_") or m.endswith("num_batches_tracked") for m in missing), (missing, unexpected)
+    features = [None] * 12
+    for idx, s in ((0, 1), (4, 2), (5, 4), (6, 8), (8, 16), (11, 32)):
+        features[idx] = torch.from_numpy(feats[s])[None]
+    with torch.no_grad():
+        out = dec(features, pix, pix_sphere)
+    g = {k: v[0].numpy() for k, v in out.items()}
+    g.update(pix=pix.numpy(), pix_sphere=pix_sphere.numpy(), K=K)
+    return g
+
+
 def sweep_setup():
     """Small-image stand-in of generate_novel_depths.py: 244x74 image (KITTI intrinsics / 5), stride-4 grid (61x19 rays),
     the 6 poses of sample_rel_poses(step=1.0, angle=10, max_distance=1.1)."""

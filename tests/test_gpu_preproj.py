@@ -28,15 +28,15 @@ def test_table_vs_dense_on_adversarial_points(name, prec, tol):
     dense = make_renderer(cfg, prec).predict("mlp", *args, output_type="offset").cpu().numpy()
     r = make_renderer(cfg, prec, preproject=True)
     tab = r.predict("mlp", *args, output_type="offset").cpu().numpy()
-    assert r.last_pack_launches == 18                       # 15 GEMMs + 3 blend kernels built the table
-    # the gaussian network has no table: must be untouched (bit-equal to the dense renderer's)
-    og = r.predict("mlp_gaussian", *args, output_type="offset")
-    od = make_renderer(cfg, prec).predict("mlp_gaussian", *args, output_type="offset")
-    assert torch.equal(og, od)
+    assert r.last_pack_launches == 36                       # per network: 15 GEMMs + 3 blend kernels built its table
     err = float(np.abs(tab - dense).max())
     mag = float(max(1.0, np.abs(dense).max()))
     print("%s/%s: table vs dense raw-output max-abs-err %.3e (max |out| %.3e)" % (name, prec, err, mag))
     assert np.isfinite(tab).all() and err <= tol * mag
+    # the gaussian-proposal network has its own table (its own lin_z weights)
+    og = r.predict("mlp_gaussian", *args, output_type="offset").cpu().numpy()
+    od = make_renderer(cfg, prec).predict("mlp_gaussian", *args, output_type="offset").cpu().numpy()
+    assert np.abs(og - od).max() <= tol * float(max(1.0, np.abs(od).max()))
 
 
 @pytest.mark.parametrize("prec", ["fp32tc", "fp16"])
