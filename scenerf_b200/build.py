@@ -32,12 +32,28 @@ def have_nvcc() -> bool:
                (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"))
 
 
+HASH_PATH = os.path.join(HERE, "build", "source_hash.txt")
+
+
+def _source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "scenerf_b200.h")]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB_PATH):
+    """The library is stale when the CONTENT of csrc/ + the header differs from what it was built from (a hash recorded next to
+    the objects) -- not by modification times, which a copy to another machine does not preserve."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "scenerf_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(HASH_PATH) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -63,6 +79,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("link failed:\n" + r.stdout)
     with open(os.path.join(HERE, "build", "nvcc.log"), "w") as f:
         f.write("\n".join(log))
+    with open(HASH_PATH, "w") as f:
+        f.write(_source_hash())
     if verbose:
         print("\n".join(log))
     return LIB_PATH

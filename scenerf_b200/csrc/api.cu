@@ -206,8 +206,12 @@ size_t carve(const srf_config* cfg, int R, int d_latent, unsigned char* base, Ra
   w.depth_volume = a.take<float>((size_t)R * S);
   w.pts = a.take<float>((size_t)R * S * 3);
   w.raw = a.take<float>((size_t)R * S * 4);
-  const size_t m1 = mlp_workspace_bytes(cfg->precision, d_latent, (int)((size_t)R * S));
+  size_t m1 = mlp_workspace_bytes(cfg->precision, d_latent, (int)((size_t)R * S));
   const size_t m2 = mlp_workspace_bytes(cfg->precision, d_latent, (int)((size_t)R * G));
+  if ((cfg->flags & SRF_FLAG_SAVE_ACTIVATIONS) && cfg->precision == SRF_PREC_FP32) {       // the training forward's own scratch
+    const size_t m3 = srf::mlp_forward_save_scratch_bytes((int)((size_t)R * S));
+    if (m3 > m1) m1 = m3;
+  }
   w.mlp_ws_bytes = m1 > m2 ? m1 : m2;
   w.mlp_ws = a.take<unsigned char>(w.mlp_ws_bytes);
   w.saved_main = w.saved_gauss = nullptr;

@@ -20,7 +20,20 @@ namespace srf {
 
 constexpr int kBwdWarps = 4;
 constexpr int kMaxSB = 256;
-constexpr int kChunkB = 9472;                  // 74 row tiles of 128 x 4 column tiles of the 512-wide GEMMs = 296 CTAs = 148 SMs x 2
+// Points per pass of the GEMM chain.  Round 1 used 9472 (74 row tiles x 4 column tiles = one wave of 296 CTAs) -- and paid for it with
+// ~700 launches per 1200-ray training step; the GEMM kernels are grid-size agnostic, so a pass now covers a whole training call
+// (81.6 k points fit: ~40 KB of workspace per point) and the launch count drops ~8x.  SRF_TRAIN_CHUNK overrides (multiple of 128).
+static int chunk_b() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("SRF_TRAIN_CHUNK");
+    v = e ? atoi(e) : 98304;
+    if (v < 128) v = 128;
+    v = (v + 127) / 128 * 128;
+  }
+  return v;
+}
+#define kChunkB (chunk_b())
 constexpr size_t kSplitKFloats = (size_t)4 * 512 * 2528;     // split-K scratch of the weight-gradient GEMMs (20 MB)
 
 struct RayBwdSmem {
@@ -198,11 +211,13 @@ struct GemmOpt {
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;
   const int* skip = nullptr;
   const int* seg_flags = nullptr; int seg_mode = 0; const int* seg_off = nullptr;     // tf32 kernel: fused per-scale segments
+  float* relu_out = nullptr; int ld_relu = 0;                                         // tf32 kernel: also store max(result, 0)
 };
 // SRF_FLAG_TF32_MATMUL: NT GEMMs without operand ReLU go to the tcgen05 kind::tf32 kernel (gemm_tf32.cu); the callers
 // below arrange their operands accordingly (ReLU'd / transposed copies).  Set per call by the run_* entry points.
 static thread_local bool g_tf32 = false;
 
+static void relu_copy_2d(const float* src, int lds, float* dst, int ldd, int M, int N, cudaStream_t st);
 template <bool AT, bool BT, bool RA, bool RB>
 static void gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const GemmOpt& o,
                  cudaStream_t st) {
@@ -212,8 +227,10 @@ static void gemm(const float* A, int lda, const float* B, int ldb, float* C, int
   g.bias = o.bias; g.mask = o.mask; g.ldm = o.ldm; g.R = o.R; g.ldr = o.ldr; g.accumulate = o.accumulate;
   g.splitk_ws = o.splitk_ws; g.splitk_ws_floats = o.splitk_ws_floats; g.skip_if_zero = o.skip;
   if (o.seg_flags) { g.seg_flags = o.seg_flags; g.seg_mode = o.seg_mode; for (int i = 0; i < 6; ++i) g.seg_off[i] = o.seg_off[i]; }
+  g.relu_out = o.relu_out; g.ld_relu = o.ld_relu;
   if (g_tf32 && !AT && BT && !RA && !RB && launch_gemm_tf32(g, st) == 0) return;
   launch_gemm(g, st);
+  if (o.relu_out) relu_copy_2d(C, ldc, o.relu_out, o.ld_relu, M, N, st);      // SIMT fallback of a tf32-mode call
 }
 
 // gb[n] += sum_m dY[m][n], deterministic two-stage: kColSegs row segments (grid.y) -> part[seg][n], then a fixed-order sum
@@ -287,6 +304,10 @@ static void relu_copy(const float* src, float* dst, size_t n, cudaStream_t st) {
   relu_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), n / 4);
   ++launch_counter();
 }
+static void relu_copy_2d(const float* src, int lds, float* dst, int ldd, int M, int N, cudaStream_t st) {
+  if (lds == N && ldd == N) { relu_copy(src, dst, (size_t)M * N, st); return; }
+  for (int m = 0; m < M; ++m) relu_copy(src + (size_t)m * lds, dst + (size_t)m * ldd, (size_t)N, st);     // not used by the callers here
+}
 
 // dh[m][c] = (h3[m][c] > 0) ? sum_o g[m][o] * Wout[o][c] : 0        (lin_out backward w.r.t. its input)
 __global__ void __launch_bounds__(256)
@@ -344,6 +365,9 @@ size_t mlp_backward_workspace_bytes(int d_latent, int n_points) {
 // per-chunk scale flags (8 ints per chunk).
 struct SavedActs { float* X; float* PRE[3]; float* NET[3]; float* H3; int* flags; };
 static inline size_t n_chunks_b(int n) { return ((size_t)n + kChunkB - 1) / kChunkB; }
+size_t mlp_forward_save_scratch_bytes(int n_points) {           // two ReLU'd operand buffers of one pass (tf32 mode)
+  return (size_t)2 * (size_t)(n_points < kChunkB ? n_points : kChunkB) * kHidden * sizeof(float) + 256;
+}
 size_t mlp_saved_bytes(int d_latent, int n_points) {
   return (size_t)n_points * ((size_t)xin_ld_b(d_latent) + 7 * kHidden) * sizeof(float) + n_chunks_b(n_points) * 8 * sizeof(int) + 256;
 }
@@ -371,6 +395,7 @@ static void forward_chunk(const DevParams& p, const srf_mlp_weights& w, const fl
     if (g_tf32 && relu_scratch) {                                                                              // one launch, dead scales' k-blocks skipped in the kernel
       o = GemmOpt(); o.bias = w.lin_z_b[b]; o.R = (b == 0) ? PRE[0] : H3; o.ldr = H;
       o.seg_flags = scale_any; o.seg_mode = 1; o.seg_off = p.ch_off;
+      o.relu_out = relu_scratch; o.ld_relu = H;                                                                // relu(pre): fc_0's operand, from this epilogue
       gemm<false, true, false, false>(X, ld, w.lin_z_w[b], DL, PRE[b], H, m, H, DL, o, st);
     } else
     for (int s = 0; s < kScales; ++s) {                                                                        // pre = h + lin_z(z), one K-segment per scale
@@ -380,12 +405,11 @@ static void forward_chunk(const DevParams& p, const srf_mlp_weights& w, const fl
       gemm<false, true, false, false>(X + p.ch_off[s], ld, w.lin_z_w[b] + p.ch_off[s], DL, PRE[b], H, m, H, p.C[s], o, st);
     }
     if (g_tf32 && relu_scratch) {
-      relu_copy(PRE[b], relu_scratch, (size_t)m * H, st);
-      o = GemmOpt(); o.bias = w.fc0_b[b];
-      gemm<false, true, false, false>(relu_scratch, H, w.fc0_w[b], H, NET[b], H, m, H, H, o, st);              // net = fc_0(relu(pre))
-      relu_copy(NET[b], relu_scratch, (size_t)m * H, st);
+      float* relu2 = relu_scratch + (size_t)m * H;
+      o = GemmOpt(); o.bias = w.fc0_b[b]; o.relu_out = relu2; o.ld_relu = H;
+      gemm<false, true, false, false>(relu_scratch, H, w.fc0_w[b], H, NET[b], H, m, H, H, o, st);              // net = fc_0(relu(pre)); relu(net) on the side
       o = GemmOpt(); o.bias = w.fc1_b[b]; o.R = PRE[b]; o.ldr = H;
-      gemm<false, true, false, false>(relu_scratch, H, w.fc1_w[b], H, H3, H, m, H, H, o, st);                  // h = pre + fc_1(relu(net))
+      gemm<false, true, false, false>(relu2, H, w.fc1_w[b], H, H3, H, m, H, H, o, st);                         // h = pre + fc_1(relu(net))
     } else {
       o = GemmOpt(); o.bias = w.fc0_b[b];
       gemm<false, true, true, false>(PRE[b], H, w.fc0_w[b], H, NET[b], H, m, H, H, o, st);                     // net = fc_0(relu(pre))
@@ -402,7 +426,7 @@ int run_point_mlp_forward_save(const DevParams& p, const srf_mlp_weights& w, con
   const int ld = xin_ld_b(p.d_latent), H = kHidden;
   g_tf32 = tf32_matmul != 0;
   float* relu_scratch = reinterpret_cast<float*>(scratch);
-  if (g_tf32 && scratch_bytes < (size_t)(n < kChunkB ? n : kChunkB) * H * sizeof(float)) return -1;
+  if (g_tf32 && scratch_bytes < mlp_forward_save_scratch_bytes(n)) return -1;
   const SavedActs a = saved_view(saved_base, p.d_latent, n);
   const int c0 = launch_counter();
   int chunk = 0;

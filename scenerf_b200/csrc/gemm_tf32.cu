@@ -86,7 +86,8 @@ __device__ __forceinline__ bool seg_dead(const SegInfo& sg, int lo, int hi) {
 __global__ void __launch_bounds__(kThreads)
 gemm_tf32_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* C, int ldc, int M, int N,
                     int K, const float* __restrict__ bias, const float* __restrict__ mask, int ldm, const float* R, int ldr,
-                    int accumulate, int k_per, const int* __restrict__ skip, const __grid_constant__ SegInfo sg, int* err) {
+                    int accumulate, int k_per, const int* __restrict__ skip, const __grid_constant__ SegInfo sg, int* err,
+                    float* relu_out, int ld_relu) {
   if (skip && *skip == 0) return;
   if (sg.mode == 2 && seg_dead(sg, blockIdx.x * kBN, min(N, (int)(blockIdx.x + 1) * kBN))) return;   // dead column tile
   extern __shared__ unsigned char smem_raw[];
@@ -183,6 +184,8 @@ gemm_tf32_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float4* dst = reinterpret_cast<float4*>(C + (size_t)gm * ldc + gn);
           if (accumulate) { const float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
           *dst = o;
+          if (relu_out)          // the consumer GEMM reads its A operand as stored: hand it the ReLU'd activations directly
+            *reinterpret_cast<float4*>(relu_out + (size_t)gm * ld_relu + gn) = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
         }
       }
     }
@@ -250,6 +253,7 @@ int launch_gemm_tf32(const GemmArgs& g, cudaStream_t st) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if ((g.lda % 4) || (g.ldb % 4) || (g.ldc % 4) || (g.N % 4) || !al16(g.A) || !al16(g.B) || !al16(g.C)) return -1;
   if ((g.bias && !al16(g.bias)) || (g.mask && (!al16(g.mask) || g.ldm % 4)) || (g.R && (!al16(g.R) || g.ldr % 4))) return -1;
+  if (g.relu_out && (!al16(g.relu_out) || g.ld_relu % 4)) return -1;
   CUtensorMap tmA, tmB;
   if (!encode_f32(&tmA, g.A, g.M, g.K, g.lda) || !encode_f32(&tmB, g.B, g.N, g.K, g.ldb)) return -1;
   if (!g_tf32_err) {
@@ -265,7 +269,7 @@ int launch_gemm_tf32(const GemmArgs& g, cudaStream_t st) {
   for (int i = 0; i < 6; ++i) sg.off[i] = g.seg_off[i];
   const int tiles = grid.x * grid.y;
   int splits = 1;
-  if (g.splitk_ws && !g.bias && !g.mask && !g.R && tiles < 96 && g.K >= 1024) {
+  if (g.splitk_ws && !g.bias && !g.mask && !g.R && !g.relu_out && tiles < 96 && g.K >= 1024) {
     splits = (2 * 148 + tiles - 1) / tiles;
     if (splits > 32) splits = 32;
     while (splits > 1 && (size_t)splits * g.M * g.N > g.splitk_ws_floats) --splits;
@@ -275,14 +279,14 @@ int launch_gemm_tf32(const GemmArgs& g, cudaStream_t st) {
     splits = (g.K + k_per - 1) / k_per;
     grid.z = splits;
     tf32::gemm_tf32_nt_kernel<<<grid, tf32::kThreads, smem, st>>>(tmA, tmB, g.splitk_ws, g.N, g.M, g.N, g.K, nullptr, nullptr, 0, nullptr, 0,
-                                                                  0, k_per, g.skip_if_zero, sg, g_tf32_err);
+                                                                  0, k_per, g.skip_if_zero, sg, g_tf32_err, nullptr, 0);
     tf32::splitk_reduce_kernel<<<(g.M * g.N + 255) / 256, 256, 0, st>>>(g.splitk_ws, splits, g.C, g.ldc, g.M, g.N, g.accumulate,
                                                                         g.skip_if_zero, sg);
     launch_counter() += 2;
   } else {
     ++launch_counter();
     tf32::gemm_tf32_nt_kernel<<<grid, tf32::kThreads, smem, st>>>(tmA, tmB, g.C, g.ldc, g.M, g.N, g.K, g.bias, g.mask, g.ldm, g.R, g.ldr,
-                                                                  g.accumulate, g.K, g.skip_if_zero, sg, g_tf32_err);
+                                                                  g.accumulate, g.K, g.skip_if_zero, sg, g_tf32_err, g.relu_out, g.ld_relu);
   }
   return 0;
 }

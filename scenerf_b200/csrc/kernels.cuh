@@ -52,6 +52,7 @@ struct GemmArgs {
   // skipped on the device (their inputs are exact zeros / their outputs are never read).  One launch instead of five.
   const int* seg_flags = nullptr; int seg_mode = 0; int seg_off[6] = {0, 0, 0, 0, 0, 0};
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;   // optional scratch: enables deterministic split-K for long-K, few-tile shapes
+  float* relu_out = nullptr; int ld_relu = 0;   // tf32 kernel only: the epilogue also stores max(result, 0) here (the next GEMM's A operand)
 };
 int launch_gemm(const GemmArgs& g, cudaStream_t st);
 // per-thread count of kernels launched by the float32 / tf32 MLP paths (gemm.cu, gemm_tf32.cu, mlp_simt.cu, backward.cu);
@@ -76,6 +77,7 @@ void launch_lin_out(const float* Hh, const float* W, const float* bias, float* o
 // backward.cu : float32 backward of the path (reference: torch.autograd through scenerf.py:392-748)
 size_t mlp_backward_workspace_bytes(int d_latent, int n_points);
 size_t mlp_saved_bytes(int d_latent, int n_points);            // activation store of one pass (SRF_FLAG_SAVE_ACTIVATIONS)
+size_t mlp_forward_save_scratch_bytes(int n_points);           // scratch of run_point_mlp_forward_save (tf32 mode: two ReLU'd operand buffers)
 int run_point_mlp_forward_save(const DevParams& p, const srf_mlp_weights& w, const float* pts, const float* viewdir, int n, int n_per,
                                float* raw_out, int32_t* dbg_sphere, void* saved_base, int tf32_matmul, void* scratch, size_t scratch_bytes,
                                cudaStream_t st);

@@ -417,7 +417,9 @@ __device__ __forceinline__ size_t chunk_image_offset(int l, int k, int kz, int p
 // ---------------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int CG, bool PROF, bool H16, bool SPLIT>
+// PRE: the latent-table variant (a.preproj set): no lin_z chunk exists in the tile program and the E1 epilogues add table rows.
+// A template parameter so that the dense kernels carry none of that code (it cost them 3-5 % as a runtime branch).
+template <int CG, bool PROF, bool H16, bool SPLIT, bool PRE>
 __global__ void __launch_bounds__(kThreads, 1)
 point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__ KernelArgs a,
                     const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_out) {
@@ -536,7 +538,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       } prod{images, smem_base, bar0, kz, crank, a.error_flag, Ring(), l2_policy_evict_last(), &tm_main, &tm_out, a.use_tmap != 0};
       uint32_t meta_phase = 0;
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
-        uint64_t mask = a.preproj ? 0ull : ~0ull;              // pre-projected latents: no lin_z chunk is executed
+        uint64_t mask = PRE ? 0ull : ~0ull;                    // pre-projected latents: no lin_z chunk is executed
         if (a.skip_zero) {
           mbar_wait(meta_full, meta_phase, a.error_flag);        // this tile group's chunk mask is published
           meta_phase ^= 1;
@@ -638,7 +640,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             make_idesc(kTileM * CG, kMmaN), make_idesc(kTileM * CG, kOutN), 0, 0, PROF && a.prof != nullptr};
       uint32_t meta_phase = 0;
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
-        uint64_t mask = a.preproj ? 0ull : ~0ull;
+        uint64_t mask = PRE ? 0ull : ~0ull;
         if (a.skip_zero) {
           mbar_wait(meta_full, meta_phase, a.error_flag);
           meta_phase ^= 1;
@@ -668,7 +670,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       } rel{bar0, a.error_flag, Ring()};
       uint32_t meta_phase = 0;
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
-        uint64_t mask = a.preproj ? 0ull : ~0ull;
+        uint64_t mask = PRE ? 0ull : ~0ull;
         if (a.skip_zero) {
           mbar_wait(meta_full, meta_phase, a.error_flag);
           meta_phase ^= 1;
@@ -756,7 +758,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       };
       if (it == 0 || a.debug_layer >= 0) geometry(grp_i, it);
       const short2* sph_cur = sph_smem + (it & 1) * kTileM;
-      uint64_t mask = a.preproj ? 0ull : ~0ull;
+      uint64_t mask = PRE ? 0ull : ~0ull;
       if (a.skip_zero) {
         if (wt == 0) mask_smem[(it + 1) & 1] = 0ull;          // buffer of the NEXT tile group (filled later in this tile)
         mbar_wait(meta_full, meta_phase, a.error_flag);
@@ -766,7 +768,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       named_bar_sync(1, kWorkerThreads);          // sph_smem visible to all workers
       // pre-projected latents: table row of the point this lane finishes in the epilogues (zero row outside the grid)
       const unsigned char* pre_row = nullptr;
-      if (a.preproj) {
+      if constexpr (PRE) {
         const short2 sp = sph_cur[SPLIT ? ((q4 & 1) * 32 + lane) : erow];
         const bool in = sp.x >= 0 && sp.x < a.pre_W1 && sp.y >= 0 && sp.y < a.pre_H1;
         const size_t ridx = in ? (size_t)sp.y * a.pre_W1 + sp.x : (size_t)a.pre_W1 * a.pre_H1;
@@ -838,7 +840,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
             const short2 sp16 = sph_cur[xrow];
             const int2 sp = make_int2(sp16.x, sp16.y);
             const int esz = p.feat_fp16 ? 2 : 4;
-            if (a.preproj) {
+            if constexpr (PRE) {
               // warm L2 with this point's table row (3 x 512 values): the E1 epilogues read it thousands of cycles later
               if (sp.x >= 0 && sp.x < a.pre_W1 && sp.y >= 0 && sp.y < a.pre_H1) {
                 constexpr int kRowBytes = SRF_NUM_BLOCKS * kHidden * (SPLIT ? 4 : 2);
@@ -1104,7 +1106,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           }
         };
         // pre-projected latents (E1 only: write_h): 16 fp16 table values of this row per group, loaded one group ahead
-        const bool use_p = write_h && pre_row != nullptr;
+        const bool use_p = PRE && write_h;
         const uint4* prow16 = reinterpret_cast<const uint4*>(pre_row + (size_t)bias_idx * kHidden * 2);
         uint4 pn[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
         if (use_p) { pn[0] = __ldg(prow16 + (col0 >> 3)); pn[1] = __ldg(prow16 + (col0 >> 3) + 1); }
@@ -1216,7 +1218,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           for (int j = 0; j < 2; ++j)
             dst[j] = use_h ? scratch4[(size_t)((c >> 2) + 2 * mine + j) * kTileM + prow] : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        const bool use_p = write_h && pre_row != nullptr;       // pre-projected latents: 8 fp32 table values per group, one group ahead
+        const bool use_p = PRE && write_h;                      // pre-projected latents: 8 fp32 table values per group, one group ahead
         const float4* prow32 = reinterpret_cast<const float4*>(pre_row + (size_t)bias_idx * kHidden * 4);
         float4 pn[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
         if (use_p) { pn[0] = __ldg(prow32 + (col0 >> 2) + 2 * mine); pn[1] = __ldg(prow32 + (col0 >> 2) + 2 * mine + 1); }
@@ -1312,7 +1314,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
 
       // ---------------- the tile program (worker side; MMA side: walk_tile) -------------------------------------
       lap(0);
-      const bool do_gather = a.preproj == nullptr;                // latent table: no lin_z chunk exists, nothing to gather or sync
+      constexpr bool do_gather = !PRE;                            // latent table: no lin_z chunk exists, nothing to gather or sync
       if (do_gather) gather_pass(0);                              // lin_z0
       if (a.debug_layer == 1) { dump_acc(true); continue; }
       bool stop = false;
@@ -1603,20 +1605,19 @@ static bool tc_use_tmap() {
 }
 
 using TcKernelFn = void (*)(const DevParams, const tc::KernelArgs, const CUtensorMap, const CUtensorMap);
-constexpr int kNumTcKernels = 12;
-// index: bit 0 = CTA pairs, bit 1 = profiling counters, then 0 = fp32 hidden state, 4 = fp16 hidden state, 8 = split mode
+constexpr int kNumTcKernels = 24;
+// index: bit 0 = CTA pairs, bit 1 = profiling counters, then 0 = fp32 hidden state, 4 = fp16 hidden state, 8 = split mode; +12 = latent table
+#define SRF_TC_ROW(H16_, SPLIT_, PRE_)                                                                              \
+  tc::point_mlp_tc_kernel<1, false, H16_, SPLIT_, PRE_>, tc::point_mlp_tc_kernel<2, false, H16_, SPLIT_, PRE_>,     \
+  tc::point_mlp_tc_kernel<1, true, H16_, SPLIT_, PRE_>, tc::point_mlp_tc_kernel<2, true, H16_, SPLIT_, PRE_>
 static TcKernelFn tc_kernel_at(int i) {
   static const TcKernelFn table[kNumTcKernels] = {
-      tc::point_mlp_tc_kernel<1, false, false, false>, tc::point_mlp_tc_kernel<2, false, false, false>,
-      tc::point_mlp_tc_kernel<1, true, false, false>,  tc::point_mlp_tc_kernel<2, true, false, false>,
-      tc::point_mlp_tc_kernel<1, false, true, false>,  tc::point_mlp_tc_kernel<2, false, true, false>,
-      tc::point_mlp_tc_kernel<1, true, true, false>,   tc::point_mlp_tc_kernel<2, true, true, false>,
-      tc::point_mlp_tc_kernel<1, false, false, true>,  tc::point_mlp_tc_kernel<2, false, false, true>,
-      tc::point_mlp_tc_kernel<1, true, false, true>,   tc::point_mlp_tc_kernel<2, true, false, true>};
+      SRF_TC_ROW(false, false, false), SRF_TC_ROW(true, false, false), SRF_TC_ROW(false, true, false),
+      SRF_TC_ROW(false, false, true),  SRF_TC_ROW(true, false, true),  SRF_TC_ROW(false, true, true)};
   return table[i];
 }
-static TcKernelFn tc_kernel(int cg, bool prof, bool h16, bool split) {
-  return tc_kernel_at((cg == 2 ? 1 : 0) | (prof ? 2 : 0) | (split ? 8 : (h16 ? 4 : 0)));
+static TcKernelFn tc_kernel(int cg, bool prof, bool h16, bool split, bool pre = false) {
+  return tc_kernel_at((cg == 2 ? 1 : 0) | (prof ? 2 : 0) | (split ? 8 : (h16 ? 4 : 0)) + (pre ? 12 : 0));
 }
 
 static int tc_cta_group() {
@@ -1724,7 +1725,7 @@ int run_point_mlp_tc_debug(const DevParams& p, const srf_mlp_weights& w, const f
         encode_image_map(&tm_out, img + (img_bytes - out_bytes), out_bytes / 128, tc::kOutN / 2))
       a.use_tmap = 1;
   }
-  cudaLaunchKernelEx(&cfg, tc_kernel(cg, prof_env, a.hidden_fp16 != 0, split), p, a, tm_main, tm_out);
+  cudaLaunchKernelEx(&cfg, tc_kernel(cg, prof_env, a.hidden_fp16 != 0, split, a.preproj != nullptr), p, a, tm_main, tm_out);
   if (prof_env) {            // diagnostics only: synchronises and prints mean per-CTA cycle counters
     static unsigned long long host[256 * 16];
     cudaStreamSynchronize(st);
