@@ -970,7 +970,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="B", choices=["A", "B", "C", "D", "E", "sweep", "train"])
+    ap.add_argument("--workload", default="B", choices=["A", "B", "C", "D", "E", "sweep", "train", "decoder"])
     ap.add_argument("--train-matmul", default="fp32", choices=["fp32", "tf32"], help="--workload train: GEMM engine")
     ap.add_argument("--sweep-poses", type=int, default=63)
     ap.add_argument("--sweep-scale", type=int, default=2)
@@ -991,7 +991,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        if args.workload in ("D", "E", "sweep", "train"):
+        if args.workload in ("D", "E", "sweep", "train", "decoder"):
             args.workload = "B"
         run_reference(args, rank, world)
         return
@@ -1007,7 +1007,69 @@ def main():
     if args.workload == "D":
         run_D(args, rank, world, local_rank)
         return
+    if args.workload == "decoder":
+        run_decoder(args, rank, world, local_rank)
+        return
     run_render(args, rank, world, local_rank)
+
+
+def run_decoder(args, rank, world, local_rank):
+    """--workload decoder: the producer tail.  One step = DecoderSphere.forward of ONE KITTI image at the reference's
+    real sizes (EfficientNet-B7 maps of a 1220x370 image, num_features = bottleneck = 2560, sphere grid 1500x452) through
+    scenerf_b200.decoder.SphereDecoderB200: conv2 (PyTorch), 6 sphere resamplings, 5 x (upsample+concat, 7 implicit-GEMM convolutions),
+    the last convolution of each level writing the packed fp32 + fp16 pyramid.  Synthetic weights, maps and pixel->sphere table."""
+    import torch
+    from scenerf_b200 import synth
+    from scenerf_b200.decoder import SphereDecoderB200
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    W, H, oW, oH, F = 1220, 370, 1500, 452, 2560
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3)
+    rnd = lambda *sh: torch.randn(sh, generator=gen, device=dev)
+    state = {}
+    state["conv2.weight"] = rnd(F, F, 1, 1) * (2.0 / F) ** 0.5
+    state["conv2.bias"] = rnd(F) * 0.1
+    flop = 0.0
+    dims = {s: (round(oH / s), round(oW / s)) for s in (1, 2, 4, 8, 16)}
+    for s, (cin, cout) in synth.decoder_level_channels(F).items():
+        pre = "up%d._net." % s
+        px = dims[s][0] * dims[s][1]
+        state[pre + "0.weight"] = rnd(cout, cin, 3, 3) * (2.0 / (9 * cin)) ** 0.5
+        state[pre + "0.bias"] = rnd(cout) * 0.1
+        flop += 2.0 * 9 * cin * cout * px
+        for blk in (1, 2, 3):
+            for cb in (1, 2):
+                n = pre + "%d.conv_block%d" % (blk, cb)
+                state[n + ".0.weight"] = rnd(cout, cout, 3, 3) * (2.0 / (9 * cout)) ** 0.5
+                state[n + ".0.bias"] = rnd(cout) * 0.1
+                state[n + ".1.weight"] = 1.0 + 0.1 * rnd(cout)
+                state[n + ".1.bias"] = 0.1 * rnd(cout)
+                state[n + ".1.running_mean"] = 0.1 * rnd(cout)
+                state[n + ".1.running_var"] = 1.0 + 0.2 * torch.rand(cout, generator=gen, device=dev)
+                flop += 2.0 * 9 * cout * cout * px
+    dec = SphereDecoderB200(state, oW, oH, device=dev, emit_fp16=True)
+    del state
+    chans = {1: 3, 2: 32, 4: 48, 8: 80, 16: 224, 32: F}
+    features = [None] * 12
+    for idx, sc in ((0, 1), (4, 2), (5, 4), (6, 8), (8, 16), (11, 32)):
+        features[idx] = rnd(1, chans[sc], -(-H // sc), -(-W // sc))
+    ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+    pix = torch.stack([xs.reshape(-1), ys.reshape(-1)], 1).float()
+    pix_sphere = torch.stack([torch.round(pix[:, 0] * ((oW - 1) / (W - 1))), torch.round(pix[:, 1] * ((oH - 1) / (H - 1)))], 1).long()
+    ms = time_loop(lambda: dec(features, pix, pix_sphere), args.steps, args.warmup, torch.cuda.synchronize)
+    peaks = load_peaks()
+    peak = float(peaks.get("bf16_tflops_sustained") or 1400.0) / 2.0
+    if rank == 0:
+        print(json.dumps({"metric": "decoder images/sec (DecoderSphere.forward of one 1220x370 KITTI image -> packed 1500x452 pyramid)",
+                          "value": 1e3 / ms, "unit": "images/s", "ms_per_step": ms, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                          "dtype": "tf32 operands (rounded to nearest), fp32 storage and accumulate", "data": "synthetic", "higher_is_better": True,
+                          "gpu_launches": int(dec.launches) + 18,
+                          "roofline": {"bound": "tensor (tcgen05 kind::tf32; peak = measured bf16 sustained / 2)", "achieved": flop / (ms * 1e-3) / 1e12,
+                                       "peak": peak, "unit": "TFLOP/s", "frac": flop / (ms * 1e-3) / 1e12 / peak,
+                                       "algorithmic_flop_per_step": flop,
+                                       "note": "whole step incl. conv2 (PyTorch), the sphere resamplings and the upsample+concat kernels; "
+                                               "algorithmic flops = 2*9*Cin*Cout per output pixel of the 35 convolutions"}}))
 
 
 def run_D(args, rank, world, local_rank):

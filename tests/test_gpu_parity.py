@@ -180,3 +180,43 @@ def test_properties_at_scale_philox():
     assert (a["gaussian_stds"] >= 1.5).all() and (a["gaussian_means"] >= 1.5).all()
     m = a["gaussian_means"].mean(0).cpu().numpy()
     assert (np.diff(m) > 0).all()
+
+
+def test_pyramid_cache_never_reuses_a_stale_pack():
+    """Two different images through the SAME renderer must never share a pack: the cache key holds the caller's tensor objects
+    (their storage cannot be recycled under the key), inputs that need a copy (fp16 / non-contiguous maps) included, and an
+    in-place update bumps the version counter."""
+    import torch
+    cfg, seed = RENDER_CASES["kitti_mini"]
+    g = load_golden("kitti_mini")
+    K, T = torch.from_numpy(cfg.K), torch.from_numpy(cfg.T)
+    pix = torch.from_numpy(g["pixels"])
+    noise = (torch.from_numpy(g["noise_u"]), torch.from_numpy(g["noise_n"]))
+    shared = make_renderer(cfg, "fp32")
+
+    def fresh(x):
+        return make_renderer(cfg, "fp32").render_rays_batch(K, T, x, sampled_pixels=pix, noise=noise)["depth"]
+
+    def image(s, kind):
+        x = {k: torch.from_numpy(v).to("cuda:0") for k, v in pyramid_for(cfg, seed).items()}
+        x = {k: v * (1.0 + 0.25 * s) for k, v in x.items()}
+        if kind == "half":
+            return {k: v.half() for k, v in x.items()}                       # needs a dtype copy
+        if kind == "strided":
+            return {k: torch.cat([v, v], 2)[:, :, :v.shape[2]] for k, v in x.items()}      # non-contiguous view
+        return x
+
+    for i, kind in enumerate(["half", "half", "strided", "strided", "plain", "half"]):
+        x = image(i, kind)
+        got = shared.render_rays_batch(K, T, x, sampled_pixels=pix, noise=noise)["depth"]
+        assert torch.equal(got, fresh(x)), (i, kind)
+        del x                                                                 # the next image may be allocated at the same address
+        torch.cuda.empty_cache()
+    x = image(7, "plain")
+    a = shared.render_rays_batch(K, T, x, sampled_pixels=pix, noise=noise)["depth"].clone()
+    x["1_1"].mul_(1.5)                                                        # in-place: same storage, new version
+    b = shared.render_rays_batch(K, T, x, sampled_pixels=pix, noise=noise)["depth"]
+    assert not torch.equal(a, b) and torch.equal(b, fresh(x))
+    x["1_1"].data.mul_(0.5)                                                   # bypasses the version counter: needs invalidate_pyramid()
+    shared.invalidate_pyramid()
+    assert torch.equal(shared.render_rays_batch(K, T, x, sampled_pixels=pix, noise=noise)["depth"], fresh(x))
