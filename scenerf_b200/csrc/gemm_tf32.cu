@@ -198,6 +198,182 @@ gemm_tf32_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// v2: persistent, 128 x 256 output tiles, 4-stage ring (A 16 KB + B 32 KB per stage), two 256-column accumulators in TMEM so that
+// the epilogue of tile i runs under the main loop of tile i+1.  Why: kind::tf32 reads fp32 operands (4 B / element) from shared
+// memory, so the GEMM is bound by L2 -> SM bytes, not by the tensor pipe: a 128 x 128 x 32 step moves 32 KB per 1.05 MFLOP
+// (32 flop/B -> at ~42 B/cycle/SM of L2 bandwidth 33 % of the tf32 rate at best); 128 x 256 moves 48 KB per 2.1 MFLOP (43.7 flop/B)
+// and one CTA per SM keeps 192 KB in flight.  Same contract as gemm_tf32_nt_kernel (bias / ReLU mask / residual / accumulate /
+// ReLU'd side output, dead-scale segments, deterministic split-K); tiles are taken round-robin, n fastest (neighbouring CTAs
+// share the A rows in L2).
+constexpr int k2BN = 256, k2Stages = 4;
+constexpr uint32_t k2ABytes = kBM * kBK * 4, k2BBytes = k2BN * kBK * 4, k2StageBytes = k2ABytes + k2BBytes;      // 16 + 32 KB
+constexpr uint32_t k2Idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(k2BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* C, int ldc, int M, int N,
+                            int K, const float* __restrict__ bias, const float* __restrict__ mask, int ldm, const float* R, int ldr,
+                            int accumulate, int k_per, int splits, const int* __restrict__ skip, const __grid_constant__ SegInfo sg, int* err,
+                            float* relu_out, int ld_relu) {
+  if (skip && *skip == 0) return;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + k2Stages * k2StageBytes;            // full[4], empty[4], acc_full[2], acc_empty[2]
+  auto full = [&](int s_) { return bars + 8u * s_; };
+  auto empty = [&](int s_) { return bars + 8u * (k2Stages + s_); };
+  auto acc_full = [&](int b_) { return bars + 8u * (2 * k2Stages + b_); };
+  auto acc_empty = [&](int b_) { return bars + 8u * (2 * k2Stages + 2 + b_); };
+  const uint32_t tmem_slot = bars + 8u * (2 * k2Stages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = (M + kBM - 1) / kBM, nt = (N + k2BN - 1) / k2BN;
+  const int total = mt * nt * splits;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s_ = 0; s_ < k2Stages; ++s_) { mbar_init(full(s_), 1); mbar_init(empty(s_), 1); }
+    for (int b_ = 0; b_ < 2; ++b_) { mbar_init(acc_full(b_), 1); mbar_init(acc_empty(b_), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+
+  // tile t -> (split z, row tile m, column tile n); every role walks the same sequence and applies the same skips
+  struct Tile { int m0, n0, kbeg, kend, z; bool dead; };
+  auto tile_of = [&](int t) {
+    Tile tl;
+    const int n = t % nt, m = (t / nt) % mt;
+    tl.z = t / (nt * mt);
+    tl.m0 = m * kBM; tl.n0 = n * k2BN;
+    tl.kbeg = tl.z * k_per; tl.kend = min(K, tl.kbeg + k_per);
+    tl.dead = (sg.mode == 2) && seg_dead(sg, tl.n0, min(N, tl.n0 + k2BN));
+    return tl;
+  };
+  auto block_dead = [&](const Tile& tl, int i) {
+    return sg.mode == 1 && seg_dead(sg, tl.kbeg + i * kBK, min(tl.kend, tl.kbeg + (i + 1) * kBK));
+  };
+  auto live_blocks = [&](const Tile& tl) {
+    const int nk = (tl.kend - tl.kbeg + kBK - 1) / kBK;
+    if (sg.mode != 1) return nk;
+    int c = 0;
+    for (int i = 0; i < nk; ++i) c += block_dead(tl, i) ? 0 : 1;
+    return c;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int j = 0;                                             // stages issued so far (ring position)
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const Tile tl = tile_of(t);
+        if (tl.dead) continue;
+        const int nk = (tl.kend - tl.kbeg + kBK - 1) / kBK;
+        for (int i = 0; i < nk; ++i) {
+          if (block_dead(tl, i)) continue;
+          const int s_ = j % k2Stages;
+          mbar_wait(empty(s_), (((uint32_t)(j / k2Stages)) & 1u) ^ 1u, err);
+          mbar_arrive_expect_tx(full(s_), k2StageBytes);
+          tma_load_2d(base + s_ * k2StageBytes, &tmA, tl.kbeg + i * kBK, tl.m0, full(s_));
+          tma_load_2d(base + s_ * k2StageBytes + k2ABytes, &tmB, tl.kbeg + i * kBK, tl.n0, full(s_));
+          ++j;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int j = 0, at = 0;                                     // ring position, accumulator-tile counter
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const Tile tl = tile_of(t);
+        if (tl.dead) continue;
+        const int n_live = live_blocks(tl);
+        if (n_live == 0) continue;                           // the epilogue writes zeros without an accumulator
+        const int buf = at & 1;
+        mbar_wait(acc_empty(buf), (((uint32_t)(at >> 1)) & 1u) ^ 1u, err);       // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int i = 0; i < n_live; ++i) {
+          const int s_ = j % k2Stages;
+          mbar_wait(full(s_), ((uint32_t)(j / k2Stages)) & 1u, err);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s_ * k2StageBytes, sb = sa + k2ABytes;
+#pragma unroll
+          for (int k4 = 0; k4 < kBK / 8; ++k4)
+            umma_tf32(tmem + (uint32_t)(buf * k2BN), make_desc_sw128(sa + k4 * 32), make_desc_sw128(sb + k4 * 32), k2Idesc,
+                      (i > 0 || k4 > 0) ? 1u : 0u);
+          umma_commit(empty(s_));
+          ++j;
+        }
+        umma_commit(acc_full(buf));
+        ++at;
+      }
+    }
+  } else {
+    const int q = warp & 3;                                  // TMEM lane quarter this warp may read
+    int at = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const Tile tl = tile_of(t);
+      if (tl.dead) continue;
+      const int n_live = live_blocks(tl);
+      const int buf = at & 1;
+      if (n_live > 0) {
+        mbar_wait(acc_full(buf), ((uint32_t)(at >> 1)) & 1u, err);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      const int gm = tl.m0 + q * 32 + lane;
+      float* Cz = (splits > 1) ? C + (size_t)tl.z * M * ldc : C;
+#pragma unroll 1
+      for (int c = 0; c < k2BN / 32; ++c) {
+        if (tl.n0 + c * 32 >= N) break;                      // warp-uniform
+        uint32_t v[32];
+        if (n_live > 0) {
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * k2BN + c * 32), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int j2 = 0; j2 < 32; ++j2) v[j2] = 0u;
+        }
+        if (gm < M) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const int gn = tl.n0 + c * 32 + j4 * 4;
+            if (gn >= N) break;                              // N % 4 == 0
+            float4 o = make_float4(__uint_as_float(v[j4 * 4]), __uint_as_float(v[j4 * 4 + 1]), __uint_as_float(v[j4 * 4 + 2]),
+                                   __uint_as_float(v[j4 * 4 + 3]));
+            if (bias) { const float4 t4 = *reinterpret_cast<const float4*>(bias + gn); o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w; }
+            if (mask) {
+              const float4 t4 = *reinterpret_cast<const float4*>(mask + (size_t)gm * ldm + gn);
+              o.x = t4.x > 0.f ? o.x : 0.f; o.y = t4.y > 0.f ? o.y : 0.f; o.z = t4.z > 0.f ? o.z : 0.f; o.w = t4.w > 0.f ? o.w : 0.f;
+            }
+            if (R) { const float4 t4 = *reinterpret_cast<const float4*>(R + (size_t)gm * ldr + gn); o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w; }
+            float4* dst = reinterpret_cast<float4*>(Cz + (size_t)gm * ldc + gn);
+            if (accumulate) { const float4 t4 = *dst; o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w; }
+            *dst = o;
+            if (relu_out)
+              *reinterpret_cast<float4*>(relu_out + (size_t)gm * ld_relu + gn) = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+          }
+        }
+      }
+      if (n_live > 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty(buf)) : "memory");
+        ++at;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ part, int splits, float* __restrict__ C, int ldc, int M, int N, int accumulate,
                      const int* __restrict__ skip, const __grid_constant__ SegInfo sg) {
@@ -231,13 +407,13 @@ static EncodeTiledFn tf32_encode_fn() {
   }
   return fn;
 }
-// rows x K float32 matrix with row stride ld (elements): box = 128 rows x 32 floats, 128-byte swizzle
-static bool encode_f32(CUtensorMap* tm, const float* base, int rows, int K, int ld) {
+// rows x K float32 matrix with row stride ld (elements): box = box_rows rows x 32 floats, 128-byte swizzle
+static bool encode_f32(CUtensorMap* tm, const float* base, int rows, int K, int ld, int box_rows = tf32::kBM) {
   EncodeTiledFn fn = tf32_encode_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)tf32::kBK, (cuuint32_t)tf32::kBM};
+  const cuuint32_t box[2] = {(cuuint32_t)tf32::kBK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -245,6 +421,53 @@ static bool encode_f32(CUtensorMap* tm, const float* base, int rows, int K, int 
 
 static int* g_tf32_err = nullptr;       // mapped host flag written by the watchdog
 int tf32_watchdog_flag() { return g_tf32_err ? *reinterpret_cast<volatile int*>(g_tf32_err) : 0; }
+
+// v2 launch: persistent 128 x 256 tiles (see gemm_tf32_persistent_kernel); split-K for the long-K weight-gradient shapes
+static int launch_gemm_tf32_v2(const GemmArgs& g, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  if (!encode_f32(&tmA, g.A, g.M, g.K, g.lda) || !encode_f32(&tmB, g.B, g.N, g.K, g.ldb, tf32::k2BN)) return -1;
+  static int n_sm = 0;
+  static bool attr = false;
+  const size_t smem = (size_t)tf32::k2Stages * tf32::k2StageBytes + 1024 + 256;
+  if (!attr) {
+    cudaFuncSetAttribute(tf32::gemm_tf32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+    attr = true;
+  }
+  tf32::SegInfo sg;
+  sg.flags = g.seg_flags; sg.mode = g.seg_flags ? g.seg_mode : 0;
+  for (int i = 0; i < 6; ++i) sg.off[i] = g.seg_off[i];
+  const int mt = (g.M + tf32::kBM - 1) / tf32::kBM, nt = (g.N + tf32::k2BN - 1) / tf32::k2BN;
+  const int tiles = mt * nt;
+  int splits = 1, k_per = g.K;
+  if (g.splitk_ws && !g.bias && !g.mask && !g.R && !g.relu_out && tiles < n_sm / 2 && g.K >= 1024) {
+    splits = (n_sm + tiles - 1) / tiles;
+    if (splits > 32) splits = 32;
+    while (splits > 1 && (size_t)splits * g.M * g.N > g.splitk_ws_floats) --splits;
+    if (splits > 1) {
+      k_per = ((g.K + splits - 1) / splits + tf32::kBK - 1) / tf32::kBK * tf32::kBK;
+      splits = (g.K + k_per - 1) / k_per;
+    }
+  }
+  const int total = tiles * splits;
+  const int grid = total < n_sm ? total : n_sm;
+  if (splits > 1) {
+    tf32::gemm_tf32_persistent_kernel<<<grid, tf32::kThreads, smem, st>>>(tmA, tmB, g.splitk_ws, g.N, g.M, g.N, g.K, nullptr, nullptr, 0, nullptr,
+                                                                          0, 0, k_per, splits, g.skip_if_zero, sg, g_tf32_err, nullptr, 0);
+    tf32::splitk_reduce_kernel<<<(g.M * g.N + 255) / 256, 256, 0, st>>>(g.splitk_ws, splits, g.C, g.ldc, g.M, g.N, g.accumulate,
+                                                                        g.skip_if_zero, sg);
+    launch_counter() += 2;
+  } else {
+    ++launch_counter();
+    tf32::gemm_tf32_persistent_kernel<<<grid, tf32::kThreads, smem, st>>>(tmA, tmB, g.C, g.ldc, g.M, g.N, g.K, g.bias, g.mask, g.ldm, g.R, g.ldr,
+                                                                          g.accumulate, g.K, 1, g.skip_if_zero, sg, g_tf32_err, g.relu_out,
+                                                                          g.ld_relu);
+  }
+  return 0;
+}
 
 // Only the NT layout with un-transformed operands (at=false, bt=true, no relu_a / relu_b).  Returns 0, or -1 when the
 // shape cannot go through TMA (unaligned rows) -- the caller then falls back to launch_gemm.
@@ -254,12 +477,17 @@ int launch_gemm_tf32(const GemmArgs& g, cudaStream_t st) {
   if ((g.lda % 4) || (g.ldb % 4) || (g.ldc % 4) || (g.N % 4) || !al16(g.A) || !al16(g.B) || !al16(g.C)) return -1;
   if ((g.bias && !al16(g.bias)) || (g.mask && (!al16(g.mask) || g.ldm % 4)) || (g.R && (!al16(g.R) || g.ldr % 4))) return -1;
   if (g.relu_out && (!al16(g.relu_out) || g.ld_relu % 4)) return -1;
-  CUtensorMap tmA, tmB;
-  if (!encode_f32(&tmA, g.A, g.M, g.K, g.lda) || !encode_f32(&tmB, g.B, g.N, g.K, g.ldb)) return -1;
   if (!g_tf32_err) {
     int* h = nullptr;
     if (cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped) == cudaSuccess) { *h = 0; cudaHostGetDevicePointer(&g_tf32_err, h, 0); }
   }
+  // The persistent 128 x 256 kernel is opt-in (SRF_TF32_V2=1): on the training step it is faster on the forward shapes (4.0 vs 4.5 ms)
+  // but slower on the weight-gradient shapes, whose few large tiles quantise badly over 148 one-CTA SMs (8.6 vs 7.9 ms): 12.7 vs 12.5 ms
+  // per step in total (profiles/r2_history.md).
+  static const bool use_v2 = getenv("SRF_TF32_V2") != nullptr;
+  if (use_v2 && g.N >= 64) return launch_gemm_tf32_v2(g, st);
+  CUtensorMap tmA, tmB;
+  if (!encode_f32(&tmA, g.A, g.M, g.K, g.lda) || !encode_f32(&tmB, g.B, g.N, g.K, g.ldb)) return -1;
   static bool attr = false;
   const size_t smem = 2 * tf32::kStages * tf32::kTileBytes + 1024 + 256;
   if (!attr) { cudaFuncSetAttribute(tf32::gemm_tf32_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
