@@ -189,6 +189,45 @@ def _ref_worker_main(conn, workload_name, threads, seed):
         conn.send(("error", repr(e)))
 
 
+def effective_cpus():
+    """CPUs this process may really use: min(logical CPUs, scheduler affinity, cgroup CPU quota).  A GPU lease can be a
+    container with a CPU quota far below os.cpu_count() (the 1-GPU and 8-GPU boxes of this pool differ 3x in what the same
+    128-thread layout achieves); running more threads than the quota only oversubscribes."""
+    n = os.cpu_count() or 1
+    info = {"logical": n}
+    try:
+        aff = len(os.sched_getaffinity(0))
+        info["affinity"] = aff
+        n = min(n, aff)
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                txt = f.read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    q = float(txt[0]) / float(txt[1])
+                    info["cgroup_quota"] = q
+                    n = min(n, max(1, int(q + 0.5)))
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f2:
+                        q /= float(f2.read().split()[0])
+                    info["cgroup_quota"] = q
+                    n = min(n, max(1, int(q + 0.5)))
+            break
+        except Exception:
+            continue
+    try:
+        info["loadavg_1min"] = os.getloadavg()[0]
+    except Exception:
+        pass
+    info["effective"] = n
+    return n, info
+
+
 class ReferencePool:
     """REF_PROCS processes x (host threads / REF_PROCS) torch threads, each timing the reference's own
     SceneRF.render_rays_batch (oracle/_ref) on disjoint random rays of the workload."""
@@ -199,7 +238,7 @@ class ReferencePool:
         self.ok = ref_runner.available()
         if not self.ok:
             return
-        cores = os.cpu_count() or 8
+        cores, self.cpu_info = effective_cpus()
         self.procs = max(1, min(REF_PROCS, cores // 2))
         self.threads = max(1, cores // self.procs)
         ctx = mp.get_context("spawn")
@@ -252,6 +291,7 @@ def cpu_baseline(workload_name, cfg, pix, pyramid, target_seconds=20.0):
             times.append(pool.step(n)[0])
         v = n * pool.procs * len(times) / sum(times)
         return {"value": v, "unit": "rays/s", "cores": pool.procs * pool.threads, "kind": "reference", "cpu_model": ref_runner.cpu_model_name(),
+                "cpus": pool.cpu_info,
                 "sample": "%d steps; each step = %d concurrent calls (one per process, %d torch threads each) of the reference's "
                           "SceneRF.render_rays_batch (oracle/_ref) on %d random rays x %d samples of the workload in one chunk; %.1f s after a %.1f s warm-up step"
                           % (len(times), pool.procs, pool.threads, n, cfg.S, sum(times), t_warm)}
@@ -286,6 +326,7 @@ def run_reference(args, rank, world):
         value = n * pool.procs * len(times) / sum(times)
         ms = float(np.mean(times)) * 1e3
         cpu = {"value": value, "unit": "rays/s", "cores": pool.procs * pool.threads, "kind": "reference", "cpu_model": ref_runner.cpu_model_name(),
+               "cpus": pool.cpu_info,
                "sample": "each step = %d concurrent calls (one per process, %d torch threads each) of the reference's SceneRF.render_rays_batch "
                          "(unmodified sources in oracle/_ref through the SURVEY 8c shim) on %d random rays x %d samples of the workload in one chunk; "
                          "step times min/median/max %.2f/%.2f/%.2f s; layout fixed by profiles/r2_reference_cpu_layout_probe.log"

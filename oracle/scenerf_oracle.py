@@ -303,7 +303,8 @@ class OracleRenderer:
         # gaussians have p(z|c2) equal up to rounding, so the reference's BMU choice there is decided by the last
         # ulp of exp(); tests use this margin to leave such rays out of the loss_kl / som_vars comparison.
         srt = np.sort(p_z_c2, axis=2)
-        self.debug["som_margin"] = ((srt[:, :, -1] - srt[:, :, -2]) / srt[:, :, -1]).min(axis=1)
+        self.debug["som_margin"] = (((srt[:, :, -1] - srt[:, :, -2]) / srt[:, :, -1]).min(axis=1) if srt.shape[2] > 1
+                                    else np.full(srt.shape[0], np.inf, f32))          # one prototype: no decision to make
         new_means = np.zeros_like(means)
         new_vars = np.zeros_like(stds)
         for r in range(G):

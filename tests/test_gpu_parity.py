@@ -220,3 +220,35 @@ def test_pyramid_cache_never_reuses_a_stale_pack():
     x["1_1"].data.mul_(0.5)                                                   # bypasses the version counter: needs invalidate_pyramid()
     shared.invalidate_pyramid()
     assert torch.equal(shared.render_rays_batch(K, T, x, sampled_pixels=pix, noise=noise)["depth"], fresh(x))
+
+
+@pytest.mark.parametrize("U,G,P", [(1, 1, 1), (16, 8, 4), (128, 8, 16), (7, 3, 5)])
+def test_sample_count_extremes_vs_oracle(U, G, P):
+    """Shapes the goldens do not cover, against the oracle (itself pinned to the reference): the smallest ray (S = 2), the maximum
+    number of gaussians (8) and samples (S = 256, the documented cap), odd counts (S = 22: ragged warps, tiles straddling rays)."""
+    import torch
+    from scenerf_b200 import synth
+    cfg = synth.config_A(name="extreme", sphere_W=300, sphere_H=90, yaw_deg=10.0, tz=1.0, n_pts_uni=U, n_gaussians=G, n_pts_per_gaussian=P)
+    seed = 31
+    pm, pg = params_for(cfg)
+    R = 24
+    pix = synth.random_pixels(55, R, cfg.img_W, cfg.img_H)
+    rng = np.random.default_rng(3)
+    nu = rng.random((R, U), dtype=np.float32)
+    nn_ = rng.standard_normal((R, G * P)).astype(np.float32)
+    pyr = pyramid_for(cfg, seed)
+    ref = orc.OracleRenderer(cfg, pm, pg).render_rays_batch(cfg.K, cfg.T, pyr, pix, R, nu, nn_)
+    x_rgb = torch_pyramid(cfg, seed)
+    for prec in ("fp32", "fp32tc"):
+        out = _np(make_renderer(cfg, prec).render_rays_batch(torch.from_numpy(cfg.K), torch.from_numpy(cfg.T), x_rgb,
+                                                             sampled_pixels=torch.from_numpy(pix), ray_batch_size=R,
+                                                             noise=(torch.from_numpy(nu), torch.from_numpy(nn_))))
+        t = TOL[prec]
+        assert out["alphas"].shape == (R, U + G * P) and out["gaussian_means"].shape == (R, G)
+        assert max_err(out["depth"], ref["depth"]) <= t["depth"] * cfg.max_sample_depth, prec
+        assert max_err(out["color"], ref["color"]) <= t["color"], prec
+        for k in ("gaussian_means", "gaussian_stds", "alphas", "weights", "depth_volumes"):
+            assert max_err(out[k], ref[k]) <= _tol(ref[k], prec), (prec, k)
+    with pytest.raises(ValueError):
+        big = synth.config_A(name="too_big", sphere_W=300, sphere_H=90, n_pts_uni=129, n_gaussians=8, n_pts_per_gaussian=16)   # S = 257
+        make_renderer(big, "fp32").render_rays_batch(torch.from_numpy(cfg.K), torch.from_numpy(cfg.T), x_rgb, sampled_pixels=torch.from_numpy(pix))
