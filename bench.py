@@ -138,7 +138,7 @@ def cpu_port_rays_per_sec(cfg, pix, pyramid, target_seconds=15.0, chunk=128):
     """Fallback arm: the numpy oracle on a bounded sample of the workload's rays, fork pool over ray chunks with a
     FIXED layout (16 workers x cores/16 BLAS threads) so that boxes with the same core count agree."""
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
+    cores = effective_cpus()[0]
     workers = max(1, min(16, cores // 2))
     blas = max(1, cores // workers)
     _CPU["pyr"] = pyramid                      # inherited by fork (copy-on-write, no pickling of 281 MB)
