@@ -376,7 +376,8 @@ def run_sweep(args, rank, world, local):
     cfg = synth.config_A(name="sweep")                     # KITTI class defaults: 64 samples/ray, sphere 1500x452
     pm, pg = synth.make_model_params(cfg)
     to = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
-    r = B200Renderer(hp_from_cfg(cfg), to(pm), to(pg), device=dev, precision="fp16")
+    # the sweep renders 63 poses of ONE source frame: the per-image latent table (built once, first call) is the natural mode
+    r = B200Renderer(hp_from_cfg(cfg), to(pm), to(pg), device=dev, precision=args.precision, preproject=bool(args.sweep_table))
     x_rgb = {k: torch.from_numpy(v).to(dev) for k, v in synth.make_pyramid(3, cfg.sphere_W, cfg.sphere_H).items()}
     cam_K = torch.from_numpy(synth.KITTI_K).to(dev)
     sw = sweep.NovelDepthSweep(r, cam_K, x_rgb, img_size=(1220, 370), scale=args.sweep_scale)
@@ -436,7 +437,8 @@ def run_sweep(args, rank, world, local):
 
     out = {"metric": "sweep frames/sec (one source frame: %d poses rendered at stride %d + TSDF fusion)" % (len(poses), args.sweep_scale),
            "value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "rays_per_pose": int(sw.pixels.shape[0]), "samples_per_ray": cfg.S, "poses": len(poses),
+           "rays_per_pose": int(sw.pixels.shape[0]), "samples_per_ray": cfg.S, "poses": len(poses), "precision": args.precision,
+           "latent_table": bool(args.sweep_table),
            "rays_per_sec": len(poses) * int(sw.pixels.shape[0]) / (ms * 1e-3), "gpu_launches": sw.launches // max(1, args.steps),
            "volume": [int(d) for d in tv._vol_dim], "volume_touched_frac": float((vol.get_weight() > 0).mean()),
            "tsdf_kernel": {"us_per_launch": tsdf_us, "algorithmic_bytes": alg_bytes, "achieved_gbps": alg_bytes / (tsdf_us * 1e-6) / 1e9,
@@ -1015,6 +1017,7 @@ def main():
     ap.add_argument("--train-matmul", default="fp32", choices=["fp32", "tf32"], help="--workload train: GEMM engine")
     ap.add_argument("--sweep-poses", type=int, default=63)
     ap.add_argument("--sweep-scale", type=int, default=2)
+    ap.add_argument("--sweep-table", type=int, default=1, help="--workload sweep: 1 = use the per-image latent table (default), 0 = dense")
     ap.add_argument("--precision", default="fp32tc", choices=["fp32tc", "fp16", "fp32"],
                     help="fp32tc (default, precision-matched to the reference's fp32 sgemm), fp16 (fast mode), fp32 (strict SIMT)")
     ap.add_argument("--outputs", default="minimal", choices=["minimal", "all"], help="depth+colour (inference callers) or the full 12-key dict")

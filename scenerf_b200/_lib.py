@@ -7,7 +7,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libscenerf_b200.so")
+# SCENERF_B200_LIB: load another build of the library (kernel experiments: `python -m scenerf_b200.build --variant NAME -DFLAG`)
+LIB_PATH = os.environ.get("SCENERF_B200_LIB") or os.path.join(HERE, "libscenerf_b200.so")
+_DEFAULT_LIB = os.path.join(HERE, "libscenerf_b200.so")
 
 ABI_VERSION = 2
 NUM_SCALES = 5
@@ -132,7 +134,7 @@ def load(build_if_missing: bool = True):
             raise RuntimeError("libscenerf_b200.so is missing: run `python -m scenerf_b200.build`")
         from . import build as _build
         _build.build()
-    elif build_if_missing:
+    elif build_if_missing and LIB_PATH == _DEFAULT_LIB:
         # an edited csrc/*.cu must never run as the old binary: rebuild when a source is newer than the library
         # (skipped silently where nvcc does not exist, e.g. a deployment box that only ships the .so)
         from . import build as _build

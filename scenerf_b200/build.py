@@ -86,5 +86,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_variant(name: str, defines) -> str:
+    """An experimental build next to the product library: csrc/mlp_tc.cu recompiled with extra -D flags, linked with the
+    product's other objects into libscenerf_b200_<name>.so (select it with SCENERF_B200_LIB=<path>).  For A/B runs only."""
+    build()
+    obj = os.path.join(HERE, "build", "mlp_tc_%s.o" % name)
+    cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *defines, "-c", os.path.join(CSRC, "mlp_tc.cu"), "-o", obj]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+        raise RuntimeError("nvcc failed:\n" + r.stdout)
+    objs = [obj if s == "mlp_tc.cu" else os.path.join(HERE, "build", s.replace(".cu", ".o")) for s in SOURCES]
+    out = os.path.join(HERE, "libscenerf_b200_%s.so" % name)
+    r = subprocess.run([_nvcc(), "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+        raise RuntimeError("link failed:\n" + r.stdout)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

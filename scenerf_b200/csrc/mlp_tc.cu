@@ -1110,6 +1110,10 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         const uint4* prow16 = reinterpret_cast<const uint4*>(pre_row + (size_t)bias_idx * kHidden * 2);
         uint4 pn[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
         if (use_p) { pn[0] = __ldg(prow16 + (col0 >> 3)); pn[1] = __ldg(prow16 + (col0 >> 3) + 1); }
+#ifdef SRF_EXP_PREFETCH
+        uint4 pm[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};       // odd groups (pn: even groups): two groups ahead
+        if (use_p) { pm[0] = __ldg(prow16 + ((col0 + 16) >> 3)); pm[1] = __ldg(prow16 + ((col0 + 16) >> 3) + 1); }
+#endif
         // the operands that do not depend on the accumulator (hidden state, table row) are requested BEFORE waiting for it:
         // their L2 latency runs under the wait
         load_h(hx, col0);
@@ -1122,8 +1126,14 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         auto process = [&](int grp, float4 (&hbuf)[4]) {
           const int col = col0 + grp * 16;
           float4 bb[4], hh[4];
+#ifdef SRF_EXP_PREFETCH
+          uint4 (&pbuf)[2] = (grp & 1) ? pm : pn;
+          const uint4 pc0 = pbuf[0], pc1 = pbuf[1];
+          if (use_p && grp < 6) { pbuf[0] = __ldg(prow16 + ((col + 32) >> 3)); pbuf[1] = __ldg(prow16 + ((col + 32) >> 3) + 1); }
+#else
           const uint4 pc0 = pn[0], pc1 = pn[1];
           if (use_p && grp < 7) { pn[0] = __ldg(prow16 + ((col + 16) >> 3)); pn[1] = __ldg(prow16 + ((col + 16) >> 3) + 1); }
+#endif
 #pragma unroll
           for (int j = 0; j < 4; ++j)     // 16 KB bias header: L1-resident broadcast; a latent-table row already contains c_b
             bb[j] = use_p ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b4 + (col >> 2) + j);
