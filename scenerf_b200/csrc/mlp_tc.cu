@@ -34,6 +34,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include "kernels.cuh"
 
 namespace srf {
@@ -689,7 +690,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     float4* scratch4 = reinterpret_cast<float4*>(a.scratch + (size_t)blockIdx.x * kTileM * kHidden);
     int fa = 0;                                  // FIFO position in A bank 0 (slots 0..3): x / latent chunks
     uint32_t fill_par = 0;                       // per-slot parity of the number of fills done by the workers
-    uint32_t half_par[2] = {0, 0};
+    uint32_t half_par = 0;                                       // bit p: parity of accumulator half p's "full" barrier
     uint32_t meta_phase = 0;
     uint32_t zpar = 0;                           // parity per zbar slot
     unsigned char* zc_base = a.zcache ? a.zcache + (size_t)blockIdx.x * kZCache * kASlotBytes : nullptr;
@@ -1079,128 +1080,106 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       //   part: 0 -> columns 0..255 -> A slots 0..3 ; 1 -> columns 256..511 -> A slots 4..7.  This warp: 128 columns
       //   (2 A chunks).  bias_idx: header vector; use_h: add the fp32 hidden state from scratch; write_h: store it.
       //   16-column groups; TMEM load, scratch and bias of group g+1 are in flight while group g is processed.
-      auto epilogue_half = [&](int part, int bias_idx, bool use_h, bool write_h) {
+      // SASS of the first version of this epilogue (run-time flags, one register set copied forward): ~206 instructions per
+      // 16-column group and lane (48 FADD, 36 register MOVs from copying the prefetched operands, 32 half->float conversions,
+      // 16 packs, flag-dependent selects) for 16 elements -- with two warps per scheduler the epilogues are ISSUE-bound
+      // (2 x 206 issue slots ~ the measured 450 cycles per group), not latency-bound.  Here every flag is a compile-time
+      // constant of the call site (no selects, no +0 adds), the operands of even and odd groups live in two register sets
+      // that are consumed in place (no MOVs), and per-lane base pointers advance by constants.  The body is force-inlined:
+      // an out-of-line closure keeps every captured variable in local memory (measured: 1.4x slower epilogues).
+      auto epilogue_half_lean = [&](auto use_h_c, auto write_h_c, auto use_p_c, int part, int bias_idx) __attribute__((always_inline)) {
+        constexpr bool USE_H = decltype(use_h_c)::value, WRITE_H = decltype(write_h_c)::value, USE_P = decltype(use_p_c)::value;
         lap(1);
-        const float4* b4 = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden);
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const int col0 = part * 256 + sub * 128;
-        // Software pipeline (registers): the TMEM load of group g+1 and the scratch (fp32 hidden state, L2-resident)
-        // loads of groups g+1 and g+2 are in flight while group g is processed.
-        uint32_t vn[16];
-        float4 hx[4], hy[4];                       // hx: even groups, hy: odd groups (fp16 mode: raw halves in [0],[1])
-        constexpr bool h16 = H16;                  // hidden state carried as fp16 (SRF_FLAG_HIDDEN_FP16)
-        uint4* scratch8 = reinterpret_cast<uint4*>(scratch4);      // fp16 mode: 8 halves per uint4, [col/8][row]
-        auto load_h = [&](float4 (&dst)[4], int c) {
-          if (!use_h) {
+        const float4* bp = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden) + (col0 >> 2);        // 4 float4 per group
+        uint4* h8 = reinterpret_cast<uint4*>(scratch4) + (size_t)(col0 >> 3) * kTileM + erow;                       // fp16 h: [col/8][row], 2 per group
+        float4* h4 = scratch4 + (size_t)(col0 >> 2) * kTileM + erow;                                                // fp32 h: [col/4][row], 4 per group
+        const uint4* pp = reinterpret_cast<const uint4*>(pre_row + (size_t)bias_idx * kHidden * 2) + (col0 >> 3);   // table row: 2 uint4 per group
+        struct Set { uint32_t v[16]; uint4 h[H16 ? 2 : 4]; uint4 p[2]; };
+        Set A, B;
+        auto load_hp = [&](Set& s, int g) {                     // accumulator-independent operands of group g
+          if constexpr (USE_H) {
+            if constexpr (H16) { s.h[0] = h8[(size_t)(2 * g) * kTileM]; s.h[1] = h8[(size_t)(2 * g + 1) * kTileM]; }
+            else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          } else if (h16) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint4 raw = scratch8[(size_t)((c >> 3) + j) * kTileM + erow];
-              dst[j] = make_float4(__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w));
+              for (int j = 0; j < 4; ++j) s.h[j] = *reinterpret_cast<const uint4*>(h4 + (size_t)(4 * g + j) * kTileM);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = scratch4[(size_t)((c >> 2) + j) * kTileM + erow];
           }
+          if constexpr (USE_P) { s.p[0] = __ldg(pp + 2 * g); s.p[1] = __ldg(pp + 2 * g + 1); }
         };
-        // pre-projected latents (E1 only: write_h): 16 fp16 table values of this row per group, loaded one group ahead
-        const bool use_p = PRE && write_h;
-        const uint4* prow16 = reinterpret_cast<const uint4*>(pre_row + (size_t)bias_idx * kHidden * 2);
-        uint4 pn[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
-        if (use_p) { pn[0] = __ldg(prow16 + (col0 >> 3)); pn[1] = __ldg(prow16 + (col0 >> 3) + 1); }
-#ifdef SRF_EXP_PREFETCH
-        uint4 pm[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};       // odd groups (pn: even groups): two groups ahead
-        if (use_p) { pm[0] = __ldg(prow16 + ((col0 + 16) >> 3)); pm[1] = __ldg(prow16 + ((col0 + 16) >> 3) + 1); }
-#endif
-        // the operands that do not depend on the accumulator (hidden state, table row) are requested BEFORE waiting for it:
-        // their L2 latency runs under the wait
-        load_h(hx, col0);
-        load_h(hy, col0 + 16);
-        mbar_wait(half_full(part), half_par[part], a.error_flag);
-        half_par[part] ^= 1;
+        load_hp(A, 0);
+        load_hp(B, 1);
+        mbar_wait(half_full(part), (half_par >> part) & 1u, a.error_flag);
+        half_par ^= 1u << part;
         tc_fence_after();
         lap(2);
-        tmem_ld16(trow + (uint32_t)col0, vn);
-        auto process = [&](int grp, float4 (&hbuf)[4]) {
-          const int col = col0 + grp * 16;
-          float4 bb[4], hh[4];
-#ifdef SRF_EXP_PREFETCH
-          uint4 (&pbuf)[2] = (grp & 1) ? pm : pn;
-          const uint4 pc0 = pbuf[0], pc1 = pbuf[1];
-          if (use_p && grp < 6) { pbuf[0] = __ldg(prow16 + ((col + 32) >> 3)); pbuf[1] = __ldg(prow16 + ((col + 32) >> 3) + 1); }
-#else
-          const uint4 pc0 = pn[0], pc1 = pn[1];
-          if (use_p && grp < 7) { pn[0] = __ldg(prow16 + ((col + 16) >> 3)); pn[1] = __ldg(prow16 + ((col + 16) >> 3) + 1); }
-#endif
+        tmem_ld16(trow + (uint32_t)col0, A.v);
+        auto body = [&](Set& cur, Set& nxt, int g) __attribute__((always_inline)) {
+          const int col = col0 + g * 16;
+          float4 bb[4];
+          if constexpr (!USE_P) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)     // 16 KB bias header: L1-resident broadcast; a latent-table row already contains c_b
-            bb[j] = use_p ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b4 + (col >> 2) + j);
+            for (int j = 0; j < 4; ++j) bb[j] = __ldg(bp + 4 * g + j);
+          }
           tmem_ld_wait();
-          uint32_t v[16];
+          if (g < 7) tmem_ld16(trow + (uint32_t)(col + 16), nxt.v);
+          const int slot = col >> 6;
+          if ((g & 3) == 0) wait_slot_free(slot);
+          const uint32_t srow = smem_base + kSmemA + slot * kASlotBytes + (uint32_t)(erow * 128);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = vn[j];
-          if (use_h && h16) {
-            // unpack 16 halves (2 x uint4) -> 4 float4
+          for (int gq = 0; gq < 2; ++gq) {                      // 2 granules of 8 columns
+            float r[8];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint32_t rw[4] = {__float_as_uint(hbuf[j].x), __float_as_uint(hbuf[j].y), __float_as_uint(hbuf[j].z), __float_as_uint(hbuf[j].w)};
-              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&rw[0]));
-              const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&rw[1]));
-              const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&rw[2]));
-              const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&rw[3]));
-              hh[2 * j] = make_float4(f0.x, f0.y, f1.x, f1.y);
-              hh[2 * j + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+            for (int e = 0; e < 8; ++e) r[e] = __uint_as_float(cur.v[gq * 8 + e]);
+            if constexpr (!USE_P) {
+              const float4 b0 = bb[2 * gq], b1 = bb[2 * gq + 1];
+              r[0] += b0.x; r[1] += b0.y; r[2] += b0.z; r[3] += b0.w; r[4] += b1.x; r[5] += b1.y; r[6] += b1.z; r[7] += b1.w;
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) hh[j] = hbuf[j];
-          }
-          if (grp < 7) tmem_ld16(trow + (uint32_t)(col + 16), vn);
-          if (use_h && grp < 6) load_h(hbuf, col + 32);
-          const int slot = col >> 6;                              // A chunk k lives in slot k
-          if ((grp & 3) == 0) wait_slot_free(slot);
-          const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
-#pragma unroll
-          for (int gq = 0; gq < 2; ++gq) {                        // 2 granules of 8 columns
-            float4 r[2];
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int j = gq * 2 + half;
-              r[half].x = __uint_as_float(v[j * 4 + 0]) + bb[j].x + hh[j].x;
-              r[half].y = __uint_as_float(v[j * 4 + 1]) + bb[j].y + hh[j].y;
-              r[half].z = __uint_as_float(v[j * 4 + 2]) + bb[j].z + hh[j].z;
-              r[half].w = __uint_as_float(v[j * 4 + 3]) + bb[j].w + hh[j].w;
-              if (use_p) {
-                const uint4 pq = gq ? pc1 : pc0;                  // 8 halves of granule gq; this float4 = words (2*half, 2*half+1)
-                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(half ? &pq.z : &pq.x));
-                const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(half ? &pq.w : &pq.y));
-                r[half].x += f0.x; r[half].y += f0.y; r[half].z += f1.x; r[half].w += f1.y;
+            if constexpr (USE_H) {
+              if constexpr (H16) {
+                const uint4 hq = cur.h[gq];
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&hq.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&hq.y));
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&hq.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&hq.w));
+                r[0] += f0.x; r[1] += f0.y; r[2] += f1.x; r[3] += f1.y; r[4] += f2.x; r[5] += f2.y; r[6] += f3.x; r[7] += f3.y;
+              } else {
+                const uint4 ha = cur.h[2 * gq], hb = cur.h[2 * gq + 1];
+                r[0] += __uint_as_float(ha.x); r[1] += __uint_as_float(ha.y); r[2] += __uint_as_float(ha.z); r[3] += __uint_as_float(ha.w);
+                r[4] += __uint_as_float(hb.x); r[5] += __uint_as_float(hb.y); r[6] += __uint_as_float(hb.z); r[7] += __uint_as_float(hb.w);
               }
-              if (write_h && !h16) scratch4[(size_t)((col >> 2) + j) * kTileM + erow] = r[half];
             }
-            if (write_h && h16)
-              scratch8[(size_t)((col >> 3) + gq) * kTileM + erow] =
-                  make_uint4(pack_half2(r[0].x, r[0].y), pack_half2(r[0].z, r[0].w), pack_half2(r[1].x, r[1].y), pack_half2(r[1].z, r[1].w));
-            const int gcol = ((col & 63) >> 3) + gq;              // granule inside the 64-wide chunk
-            sts128(slot_addr + sw128_offset(erow, gcol), pack_relu_half2(r[0].x, r[0].y), pack_relu_half2(r[0].z, r[0].w),
-                   pack_relu_half2(r[1].x, r[1].y), pack_relu_half2(r[1].z, r[1].w));
+            if constexpr (USE_P) {
+              const uint4 pq = cur.p[gq];
+              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&pq.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&pq.y));
+              const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&pq.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&pq.w));
+              r[0] += f0.x; r[1] += f0.y; r[2] += f1.x; r[3] += f1.y; r[4] += f2.x; r[5] += f2.y; r[6] += f3.x; r[7] += f3.y;
+            }
+            if constexpr (WRITE_H) {
+              if constexpr (H16)
+                h8[(size_t)(2 * g + gq) * kTileM] = make_uint4(pack_half2(r[0], r[1]), pack_half2(r[2], r[3]), pack_half2(r[4], r[5]), pack_half2(r[6], r[7]));
+              else {
+                h4[(size_t)(4 * g + 2 * gq) * kTileM] = make_float4(r[0], r[1], r[2], r[3]);
+                h4[(size_t)(4 * g + 2 * gq + 1) * kTileM] = make_float4(r[4], r[5], r[6], r[7]);
+              }
+            }
+            const int gcol = ((col & 63) >> 3) + gq;            // granule inside the 64-wide chunk; swizzle: granule ^ (row & 7)
+            sts128(srow + (uint32_t)(((gcol ^ (erow & 7)) << 4)), pack_relu_half2(r[0], r[1]), pack_relu_half2(r[2], r[3]),
+                   pack_relu_half2(r[4], r[5]), pack_relu_half2(r[6], r[7]));
           }
+          if (g < 6) load_hp(cur, g + 2);                       // this set's next group
         };
-        for (int grp = 0; grp < 8; grp += 2) {
-          process(grp, hx);
-          process(grp + 1, hy);
+#pragma unroll 1
+        for (int g = 0; g < 8; g += 2) {
+          body(A, B, g);
+          body(B, A, g + 1);
         }
-        // every TMEM read and smem write of this warp for this half is done: publish the 4 A chunks of the half.
-        // (Every warp arrives on all 4, so "chunk k full" also means "the whole half has been drained from TMEM".)
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0)
-          for (int s = 4 * part; s < 4 * part + 4; ++s) arrive_a_full(s);
+          for (int s_ = 4 * part; s_ < 4 * part + 4; ++s_) arrive_a_full(s_);
         fill_par ^= 0xFu << (4 * part);
-        lap(write_h ? 3 : (use_h ? 6 : 5));
+        lap(WRITE_H ? 3 : (USE_H ? 6 : 5));
       };
 
       // ---------------- split mode: the same epilogue for a 64-point tile --------------------------------------------
@@ -1212,100 +1191,132 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       //   finished operands (granule g or g+1 of rows r and r+64), so no staging buffer exists; one 64-thread named
       //   barrier per group orders the hand-over.  Both warps then do the same arithmetic on their 8 columns:
       //   (D_hi + D_lo) * 2^-s + bias (+ h), ReLU, hi/lo split, two 16-byte A-tile stores.
-      auto epilogue_half_split = [&](int part, int bias_idx, bool use_h, bool write_h) {
+      //   Flags AND the warp's role (hi / lo lanes) are compile-time, operands of even / odd groups in two register sets.
+      auto epilogue_split_lean = [&](auto mine_c, auto use_h_c, auto write_h_c, auto use_p_c, int part, int bias_idx) __attribute__((always_inline)) {
+        constexpr int MINE = decltype(mine_c)::value;           // 0: hi warp (lanes r), finishes columns 0-7 of a group; 1: lo warp (lanes r+64), 8-15
+        constexpr bool USE_H = decltype(use_h_c)::value, WRITE_H = decltype(write_h_c)::value, USE_P = decltype(use_p_c)::value;
         lap(1);
-        const int mine = (q4 < 2) ? 0 : 1;                      // 0: hi warp, finishes columns 0-7 of a group; 1: lo warp, 8-15
         const int pair_bar = 2 + (q4 & 1) * 2 + sub;            // named barriers 2..5: one per (hi, lo) warp pair
         const int prow = (q4 & 1) * 32 + lane;                  // point row (0..63) of this lane
-        const float4* b4 = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden);
         const float inv_scale = __ldg(bias + kInvScaleSlot);
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
         const int col0 = part * 256 + sub * 128;
-        uint32_t vn[16];
-        float4 hn[2];
-        auto load_h = [&](float4 (&dst)[2], int c) {            // this warp's 8 columns of group starting at column c
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            dst[j] = use_h ? scratch4[(size_t)((c >> 2) + 2 * mine + j) * kTileM + prow] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* bp = reinterpret_cast<const float4*>(bias + (size_t)bias_idx * kHidden) + (col0 >> 2) + 2 * MINE;          // + 4 per group
+        float4* hp = scratch4 + (size_t)((col0 >> 2) + 2 * MINE) * kTileM + prow;                                              // + 4*kTileM per group
+        const float4* pp4 = reinterpret_cast<const float4*>(pre_row + (size_t)bias_idx * kHidden * 4) + (col0 >> 2) + 2 * MINE;  // + 4 per group
+        struct Set { uint32_t v[16]; float4 h[2]; float4 p[2]; };
+        Set A, B;
+        auto load_hp = [&](Set& s_, int g) __attribute__((always_inline)) {
+          if constexpr (USE_H) { s_.h[0] = hp[(size_t)(4 * g) * kTileM]; s_.h[1] = hp[(size_t)(4 * g + 1) * kTileM]; }
+          if constexpr (USE_P) { s_.p[0] = __ldg(pp4 + 4 * g); s_.p[1] = __ldg(pp4 + 4 * g + 1); }
         };
-        const bool use_p = PRE && write_h;                      // pre-projected latents: 8 fp32 table values per group, one group ahead
-        const float4* prow32 = reinterpret_cast<const float4*>(pre_row + (size_t)bias_idx * kHidden * 4);
-        float4 pn[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-        if (use_p) { pn[0] = __ldg(prow32 + (col0 >> 2) + 2 * mine); pn[1] = __ldg(prow32 + (col0 >> 2) + 2 * mine + 1); }
-        load_h(hn, col0);                                       // accumulator-independent operands first: latency under the wait
-        mbar_wait(half_full(part), half_par[part], a.error_flag);
-        half_par[part] ^= 1;
+        load_hp(A, 0);
+        load_hp(B, 1);
+        mbar_wait(half_full(part), (half_par >> part) & 1u, a.error_flag);
+        half_par ^= 1u << part;
         tc_fence_after();
         lap(2);
-        tmem_ld16(trow + (uint32_t)col0, vn);
-        for (int grp = 0; grp < 8; ++grp) {
-          const int col = col0 + grp * 16;
+        tmem_ld16(trow + (uint32_t)col0, A.v);
+        auto body = [&](Set& cur, Set& nxt, int g) __attribute__((always_inline)) {
+          const int col = col0 + g * 16;
           const int slot = col >> 6;
-          const float ppv[8] = {pn[0].x, pn[0].y, pn[0].z, pn[0].w, pn[1].x, pn[1].y, pn[1].z, pn[1].w};
-          if (use_p && grp < 7) { pn[0] = __ldg(prow32 + ((col + 16) >> 2) + 2 * mine); pn[1] = __ldg(prow32 + ((col + 16) >> 2) + 2 * mine + 1); }
-          if ((grp & 3) == 0) wait_slot_free(slot);
+          if ((g & 3) == 0) wait_slot_free(slot);
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
           const int gcol = (col & 63) >> 3;
           // mine0/mine1: granule of THIS warp's 8 columns in rows r / r+64 ; peer0/peer1: granule of the partner's columns
-          const uint32_t mine0 = slot_addr + sw128_offset(prow, gcol + mine), mine1 = slot_addr + sw128_offset(prow + kPts, gcol + mine);
-          const uint32_t peer0 = slot_addr + sw128_offset(prow, gcol + 1 - mine), peer1 = slot_addr + sw128_offset(prow + kPts, gcol + 1 - mine);
-          float4 bb[2], hh[2];
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {     // a latent-table row already contains the cumulative bias c_b
-            bb[j] = use_p ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b4 + (col >> 2) + 2 * mine + j);
-            hh[j] = hn[j];
-          }
+          const uint32_t mine0 = slot_addr + sw128_offset(prow, gcol + MINE), mine1 = slot_addr + sw128_offset(prow + kPts, gcol + MINE);
+          const uint32_t peer0 = slot_addr + sw128_offset(prow, gcol + 1 - MINE), peer1 = slot_addr + sw128_offset(prow + kPts, gcol + 1 - MINE);
+          float4 bb[2];
+          if constexpr (!USE_P) { bb[0] = __ldg(bp + 4 * g); bb[1] = __ldg(bp + 4 * g + 1); }
           tmem_ld_wait();
-          uint32_t v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = vn[j];
-          if (grp < 7) { tmem_ld16(trow + (uint32_t)(col + 16), vn); load_h(hn, col + 16); }
-          // send the 8 partial sums the partner finishes, keep the other 8
-          uint32_t snd[8], keep[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { snd[j] = mine ? v[j] : v[8 + j]; keep[j] = mine ? v[8 + j] : v[j]; }
-          sts128(peer0, snd[0], snd[1], snd[2], snd[3]);
-          sts128(peer1, snd[4], snd[5], snd[6], snd[7]);
+          if (g < 7) tmem_ld16(trow + (uint32_t)(col + 16), nxt.v);
+          // send the 8 partial sums the partner finishes (its columns), keep the other 8
+          constexpr int SND = MINE ? 0 : 8, KEEP = MINE ? 8 : 0;
+          sts128(peer0, cur.v[SND + 0], cur.v[SND + 1], cur.v[SND + 2], cur.v[SND + 3]);
+          sts128(peer1, cur.v[SND + 4], cur.v[SND + 5], cur.v[SND + 6], cur.v[SND + 7]);
           named_bar_sync(pair_bar, 64);
           const uint4 p0 = lds128(mine0), p1 = lds128(mine1);
-          const float pp[8] = {__uint_as_float(p0.x), __uint_as_float(p0.y), __uint_as_float(p0.z), __uint_as_float(p0.w),
+          const float pr[8] = {__uint_as_float(p0.x), __uint_as_float(p0.y), __uint_as_float(p0.z), __uint_as_float(p0.w),
                                __uint_as_float(p1.x), __uint_as_float(p1.y), __uint_as_float(p1.z), __uint_as_float(p1.w)};
-          const float bbv[8] = {bb[0].x, bb[0].y, bb[0].z, bb[0].w, bb[1].x, bb[1].y, bb[1].z, bb[1].w};
-          const float hhv[8] = {hh[0].x, hh[0].y, hh[0].z, hh[0].w, hh[1].x, hh[1].y, hh[1].z, hh[1].w};
           float r[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             // D_hi + D_lo in this order on both warps (the hi warp holds D_hi, the lo warp receives it)
-            const float dsum = mine ? (pp[j] + __uint_as_float(keep[j])) : (__uint_as_float(keep[j]) + pp[j]);
-            r[j] = dsum * inv_scale + bbv[j] + hhv[j] + ppv[j];
+            const float own = __uint_as_float(cur.v[KEEP + j]);
+            const float dsum = MINE ? (pr[j] + own) : (own + pr[j]);
+            r[j] = dsum * inv_scale;
           }
-          if (write_h) {
-            scratch4[(size_t)((col >> 2) + 2 * mine) * kTileM + prow] = make_float4(r[0], r[1], r[2], r[3]);
-            scratch4[(size_t)((col >> 2) + 2 * mine + 1) * kTileM + prow] = make_float4(r[4], r[5], r[6], r[7]);
+          if constexpr (!USE_P) {
+            r[0] += bb[0].x; r[1] += bb[0].y; r[2] += bb[0].z; r[3] += bb[0].w; r[4] += bb[1].x; r[5] += bb[1].y; r[6] += bb[1].z; r[7] += bb[1].w;
+          }
+          if constexpr (USE_H) {
+            r[0] += cur.h[0].x; r[1] += cur.h[0].y; r[2] += cur.h[0].z; r[3] += cur.h[0].w;
+            r[4] += cur.h[1].x; r[5] += cur.h[1].y; r[6] += cur.h[1].z; r[7] += cur.h[1].w;
+          }
+          if constexpr (USE_P) {
+            r[0] += cur.p[0].x; r[1] += cur.p[0].y; r[2] += cur.p[0].z; r[3] += cur.p[0].w;
+            r[4] += cur.p[1].x; r[5] += cur.p[1].y; r[6] += cur.p[1].z; r[7] += cur.p[1].w;
+          }
+          if constexpr (WRITE_H) {
+            hp[(size_t)(4 * g) * kTileM] = make_float4(r[0], r[1], r[2], r[3]);
+            hp[(size_t)(4 * g + 1) * kTileM] = make_float4(r[4], r[5], r[6], r[7]);
           }
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) split_half2(fmaxf(r[2 * j], 0.0f), fmaxf(r[2 * j + 1], 0.0f), hi[j], lo[j]);
           sts128(mine0, hi[0], hi[1], hi[2], hi[3]);
           sts128(mine1, lo[0], lo[1], lo[2], lo[3]);
+          if (g < 6) load_hp(cur, g + 2);
+        };
+#pragma unroll 1
+        for (int g = 0; g < 8; g += 2) {
+          body(A, B, g);
+          body(B, A, g + 1);
         }
         tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0)
-          for (int s = 4 * part; s < 4 * part + 4; ++s) arrive_a_full(s);
+          for (int s_ = 4 * part; s_ < 4 * part + 4; ++s_) arrive_a_full(s_);
         fill_par ^= 0xFu << (4 * part);
-        lap(write_h ? 3 : (use_h ? 6 : 5));
+        lap(WRITE_H ? 3 : (USE_H ? 6 : 5));
       };
-      auto epilogue = [&](int part, int bias_idx, bool use_h, bool write_h) {
-        if constexpr (SPLIT) epilogue_half_split(part, bias_idx, use_h, write_h);
-        else epilogue_half(part, bias_idx, use_h, write_h);
+      // run-time (role, use_h, write_h) -> the compile-time variant
+      auto epilogue_split_dispatch = [&](int part, int bias_idx, bool use_h, bool write_h) __attribute__((always_inline)) {
+        using T = std::true_type;
+        using F = std::false_type;
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        using P = std::integral_constant<bool, PRE>;
+        if (q4 < 2) {
+          if (write_h) { if (use_h) epilogue_split_lean(I0{}, T{}, T{}, P{}, part, bias_idx); else epilogue_split_lean(I0{}, F{}, T{}, P{}, part, bias_idx); }
+          else { if (use_h) epilogue_split_lean(I0{}, T{}, F{}, F{}, part, bias_idx); else epilogue_split_lean(I0{}, F{}, F{}, F{}, part, bias_idx); }
+        } else {
+          if (write_h) { if (use_h) epilogue_split_lean(I1{}, T{}, T{}, P{}, part, bias_idx); else epilogue_split_lean(I1{}, F{}, T{}, P{}, part, bias_idx); }
+          else { if (use_h) epilogue_split_lean(I1{}, T{}, F{}, F{}, part, bias_idx); else epilogue_split_lean(I1{}, F{}, F{}, F{}, part, bias_idx); }
+        }
+      };
+      auto epilogue = [&](int part, int bias_idx, bool use_h, bool write_h) __attribute__((always_inline)) {
+        using T = std::true_type;
+        using F = std::false_type;
+        if constexpr (SPLIT) epilogue_split_dispatch(part, bias_idx, use_h, write_h);
+        else {
+          // (use_h, write_h) combinations of the tile program: E1 of block 0 (F,T), E1 of blocks 1,2 (T,T), E2 (F,F), E3 (T,F);
+          // the latent table is added in the E1 epilogues only
+          if (write_h) {
+            if (use_h) epilogue_half_lean(T{}, T{}, std::integral_constant<bool, PRE>{}, part, bias_idx);
+            else epilogue_half_lean(F{}, T{}, std::integral_constant<bool, PRE>{}, part, bias_idx);
+          } else {
+            if (use_h) epilogue_half_lean(T{}, F{}, F{}, part, bias_idx);
+            else epilogue_half_lean(F{}, F{}, F{}, part, bias_idx);
+          }
+        }
       };
 
       auto dump_acc = [&](bool both_halves) {     // debug: raw accumulator of the current layer
-        mbar_wait(half_full(0), half_par[0], a.error_flag);
-        half_par[0] ^= 1;
-        if (both_halves) { mbar_wait(half_full(1), half_par[1], a.error_flag); half_par[1] ^= 1; }
+        mbar_wait(half_full(0), (half_par >> 0) & 1u, a.error_flag);
+        half_par ^= 1u << 0;
+        if (both_halves) { mbar_wait(half_full(1), (half_par >> 1) & 1u, a.error_flag); half_par ^= 1u << 1; }
         tc_fence_after();
         for (int grp = 0; grp < 8; ++grp) {
           const int col = sub * 256 + grp * 32;
@@ -1329,11 +1340,12 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
       if (a.debug_layer == 1) { dump_acc(true); continue; }
       bool stop = false;
       for (int b = 0; b < SRF_NUM_BLOCKS; ++b) {
-        epilogue(0, b, b > 0, true);                              // E1a -> A chunks 0-3 of fc_0
-        epilogue(1, b, b > 0, true);                              // E1b
+        // one call site per epilogue kind (the bodies are inlined, flags compile-time): the two accumulator halves share the code
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) epilogue(part, b, b > 0, true);          // E1a, E1b -> A chunks of fc_0
         if (a.debug_layer == 2 + 3 * b) { dump_acc(true); stop = true; break; }
-        epilogue(0, 3 + b, false, false);                         // E2a -> A chunks 0-3 of fc_1 (overlaps fc_0 S4)
-        epilogue(1, 3 + b, false, false);                         // E2b (overlaps fc_1 S1)
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) epilogue(part, 3 + b, false, false);     // E2a (overlaps fc_0 S4), E2b (overlaps fc_1 S1) -> A chunks of fc_1
         if (b < SRF_NUM_BLOCKS - 1) {
           if (do_gather) gather_pass(b + 1);                      // lin_z(b+1), consumed between fc_1 S2 and S3
           if (a.debug_layer == 4 + 3 * b) { dump_acc(true); stop = true; break; }
@@ -1344,13 +1356,13 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
         }
       }
       if (stop) continue;
-      epilogue(0, 6, true, false);                                // E3a -> A chunks of lin_out
-      epilogue(1, 6, true, false);                                // E3b
+#pragma unroll 1
+      for (int part = 0; part < 2; ++part) epilogue(part, 6, true, false);            // E3a, E3b -> A chunks of lin_out
       if (a.debug_layer == 10) { dump_acc(false); continue; }
       // ---------------- E4: out = ACC[:, :d_out] + b_out ------------------------------------------------------
       lap(1);
-      mbar_wait(half_full(0), half_par[0], a.error_flag);
-      half_par[0] ^= 1;
+      mbar_wait(half_full(0), (half_par >> 0) & 1u, a.error_flag);
+      half_par ^= 1u << 0;
       tc_fence_after();
       lap(2);
       if (sub == 0) {

@@ -6,8 +6,8 @@ VAR=$1
 SCENERF_B200_LIB=$PWD/scenerf_b200/libscenerf_b200_$VAR.so timeout 600 python -m pytest tests/test_gpu_preproj.py -q -m gpu -k "adversarial or kitti_s128" 2>&1 | tail -2
 for rep in 1 2; do for which in base $VAR; do
 if [ $which = base ]; then unset SCENERF_B200_LIB; else export SCENERF_B200_LIB=$PWD/scenerf_b200/libscenerf_b200_$VAR.so; fi
-SRF_TC_PROF=1 timeout 600 python bench.py --precision fp16 --latent-table 1 --steps 3 --warmup 3 --no-variants --no-cpu-baseline --no-extras > gpurun_out/ab_$which.json 2> gpurun_out/ab_$which.err
+SRF_TC_PROF=1 timeout 600 python bench.py --precision fp16 --latent-table ${TAB:-1} --steps 3 --warmup 3 --no-variants --no-cpu-baseline --no-extras > gpurun_out/ab_$which.json 2> gpurun_out/ab_$which.err
 python -c "
 import json;d=json.loads(open('gpurun_out/ab_$which.json').read().strip().splitlines()[-1]);print('$which rep $rep: %.1f ms  %.0f rays/s'%(d['ms_per_step'],d['value']))"
-grep prof gpurun_out/ab_$which.err | grep "CTA=3065" | tail -1 | cut -c40-330
+grep prof gpurun_out/ab_$which.err | grep -E "CTA=(3065|6130)" | tail -1 | cut -c40-330
 done; done
