@@ -132,12 +132,17 @@ __device__ __noinline__ void mbar_timeout(int* error_flag, uint32_t bar, uint32_
   __threadfence_system();
   __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
-  if (mbar_try_wait(bar, parity)) return;
+// The spin loop lives out of line: the tile program has ~170 wait sites and each inlined loop (clock reads, 64-bit compare,
+// watchdog call) was ~25 instructions -- a fifth of the kernel's code for a path that only runs while there is nothing to do.
+__device__ __noinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity, int* error_flag) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) mbar_timeout(error_flag, bar, parity);
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_spin(bar, parity, error_flag);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -198,12 +203,15 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
   return ok != 0;
 }
 // wait on a barrier that CTAs of the cluster arrive on remotely (acquire at cluster scope)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* error_flag) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_cluster_spin(uint32_t bar, uint32_t parity, int* error_flag) {
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) mbar_timeout(error_flag, bar, parity);
   }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* error_flag) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  mbar_wait_cluster_spin(bar, parity, error_flag);
 }
 
 template <int CG>
@@ -792,19 +800,21 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           const uint32_t slot_addr = smem_base + kSmemA + slot * kASlotBytes;
           float qx = 0.f, qy = 0.f, qz = 0.f;
           if (gi < a.n) { qx = a.pts[(size_t)gi * 3 + 0]; qy = a.pts[(size_t)gi * 3 + 1]; qz = a.pts[(size_t)gi * 3 + 2]; }
-          const float c3[3] = {qx, qy, qz};
           const float kPi = 3.14159274101257324f, kHalfPi = 1.57079637050628662f;
-          // value of x_in index idx (0..63) for this row: pe.py:32-43 order, then viewdir, then zeros
+          auto sel3 = [](int i, float v0, float v1, float v2) { return i == 0 ? v0 : (i == 1 ? v1 : v2); };   // no indexed register arrays
+          // value of x_in index idx (0..63) for this row: pe.py:32-43 order, then viewdir, then zeros.  idx is a RUN-TIME value
+          // (uniform per warp): the granules are produced by a rolled loop, so the kernel holds 8 copies of sinf (one per value of
+          // a granule, for ILP) instead of 36 -- each copy drags its never-taken large-argument path (~110 instructions) along.
           auto xval = [&](int idx, const float* vd) -> float {
             if (gi >= a.n) return 0.0f;
-            if (idx < 3) return c3[idx];
+            if (idx < 3) return sel3(idx, qx, qy, qz);
             if (idx < 3 + 36) {
-              const int j = idx - 3, fp = j / 3, cc = j % 3;        // fp = 2*k + phase
-              float arg = fmul(c3[cc], kPi * (float)(1 << (fp >> 1)));
+              const int j = idx - 3, fp = j / 3, cc = j - 3 * fp;    // fp = 2*k + phase
+              float arg = fmul(sel3(cc, qx, qy, qz), kPi * (float)(1 << (fp >> 1)));    // pi * 2^k: exact scaling of the fp32 constant
               if (fp & 1) arg = fadd(kHalfPi, arg);
               return sinf(arg);
             }
-            if (idx < kDX) return vd[idx - 39];
+            if (idx < kDX) return sel3(idx - 39, vd[0], vd[1], vd[2]);
             return 0.0f;
           };
           // one 16-byte granule (8 values) of row xrow; split mode: high parts to xrow, low parts to xrow + 64
@@ -823,19 +833,18 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
                      pack_half2(v[6], v[7]));
             }
           };
-          if (!xlive) {
-            // nothing: this row of the tile belongs to the thread of point row - 64
-          } else if (first) {
-#pragma unroll
-            for (int g = 0; g < 3; ++g) put_granule(g, nullptr);
-          } else {
-            float vd[3] = {0.f, 0.f, 0.f};
-            if (gi < a.n) {
-              const float* vp = a.viewdir + (size_t)(gi / a.n_per) * 3;
-              vd[0] = vp[0]; vd[1] = vp[1]; vd[2] = vp[2];
-            }
-#pragma unroll
-            for (int g = 3; g < 8; ++g) put_granule(g, vd);
+          float vd[3] = {0.f, 0.f, 0.f};
+          if (xlive && !first && gi < a.n) {
+            const float* vp = a.viewdir + (size_t)(gi / a.n_per) * 3;
+            vd[0] = vp[0]; vd[1] = vp[1]; vd[2] = vp[2];
+          }
+          if (xlive) {
+            // (a row of the tile with !xlive belongs to the thread of point row - 64)
+            const int g_end = first ? 3 : 8;
+#pragma unroll 1
+            for (int g = first ? 0 : 3; g < g_end; ++g) put_granule(g, vd);
+          }
+          if (xlive && !first) {
             // warm L2 with the taps this row will gather from the (usually in-bounds) fine scales: the gather runs
             // thousands of cycles later and then sees L2 instead of HBM latency
             const short2 sp16 = sph_cur[xrow];
