@@ -66,7 +66,8 @@ constexpr int kNumBars = 2 * kASlots + 2 * kBSlots + 3 + 4;            // a_full
 constexpr int kSmemTmemPtr = kSmemBar + kNumBars * 8;
 constexpr int kSmemMask = kSmemTmemPtr + 8;                            // 2 x uint64 active-chunk masks (double buffer)
 constexpr int kSmemSph = kSmemMask + 16;                               // 2 x short2 (sx,sy) per row: current + next tile
-constexpr int kSmemTotal = kSmemSph + 2 * kTileM * 4;
+constexpr int kSmemLayerRow = kSmemSph + 2 * kTileM * 4;              // kNumLayers x uint32: first image row of every layer (producer)
+constexpr int kSmemTotal = kSmemLayerRow + 48;
 static_assert(kSmemTotal + 1024 <= 232448, "shared memory budget");
 
 struct Layer { int chunks_is_kz, chunks, fresh, signal, is_out; };
@@ -462,6 +463,10 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     mbar_init(meta_full, kWorkerWarps);
     for (int s = 0; s < 4; ++s) mbar_init(zbar(s), 1);
     mask_smem[0] = 0ull; mask_smem[1] = 0ull;
+    // row (128-byte unit) of the first weight image of every layer inside the image region: the producer looks images up per op,
+    // and summing the layer sizes there cost it ~80 instructions per image -- on the one thread that has to keep the ring full
+    for (int l = 0; l < kNumLayers; ++l)
+      reinterpret_cast<volatile uint32_t*>(smem + kSmemLayerRow)[l] = (uint32_t)(chunk_image_offset(l, 0, a.kz, SPLIT ? 2 : 1) / 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<CG>(smem_base + kSmemTmemPtr, kTmemCols);
@@ -497,7 +502,7 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
     if (lane == 0) {
       struct Producer {
         const unsigned char* images; uint32_t smem_base, bar0; int kz; uint32_t crank; int* err; Ring rb; uint64_t policy;
-        const CUtensorMap* tmm; const CUtensorMap* tmo; bool use_tmap;
+        const CUtensorMap* tmm; const CUtensorMap* tmo; bool use_tmap; const volatile uint32_t* layer_row;
         __device__ __forceinline__ uint32_t bfull(int s) const { return bar0 + 8u * (2 * kASlots + s); }
         __device__ __forceinline__ uint32_t bempty(int s) const { return bar0 + 8u * (2 * kASlots + kBSlots + s); }
         __device__ __forceinline__ void load(const unsigned char* src, uint32_t bytes) {
@@ -521,17 +526,18 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           for (int part = 0; part < kParts; ++part) load(base + (size_t)(q * kParts + part) * kBSlotBytes, kBSlotBytes);
         }
         __device__ __forceinline__ void op(int kind, int l, int k, int h, int) {
+          // first row of chunk k of layer l (chunk_image_offset / 128)
+          const int row0 = (int)layer_row[l] + k * (kind == OP_OUT ? kOutImgBytes / 128 : kQuarters * kBSlotBytes / 128) * kParts;
           if (CG == 2 && use_tmap) {
             if (kind == OP_OUT) {
               for (int part = 0; part < kParts; ++part) load_t(tmo, (k * kParts + part) * kOutN + (int)crank * (kOutN / 2), kOutImgBytes / 2);
               return;
             }
-            const int row0 = (int)(chunk_image_offset(l, k, kz, kParts) / 128);
             if (kind == OP_KOUTER) { for (int i = 0; i < kHalves; ++i) quarter_t(row0, i * 2 + (int)crank); }
             else quarter_t(row0, 2 * h + (int)crank);
             return;
           }
-          const unsigned char* base = images + chunk_image_offset(l, k, kz, kParts);
+          const unsigned char* base = images + (size_t)row0 * 128;
           if (kind == OP_OUT) {
             for (int part = 0; part < kParts; ++part) load(base + (size_t)part * kOutImgBytes + (size_t)crank * (kOutImgBytes / CG), kOutImgBytes / CG);
             return;
@@ -544,7 +550,8 @@ point_mlp_tc_kernel(const __grid_constant__ DevParams p, const __grid_constant__
           }
         }
         __device__ __forceinline__ void ev(int) {}
-      } prod{images, smem_base, bar0, kz, crank, a.error_flag, Ring(), l2_policy_evict_last(), &tm_main, &tm_out, a.use_tmap != 0};
+      } prod{images, smem_base, bar0, kz, crank, a.error_flag, Ring(), l2_policy_evict_last(), &tm_main, &tm_out, a.use_tmap != 0,
+             reinterpret_cast<const volatile uint32_t*>(smem + kSmemLayerRow)};
       uint32_t meta_phase = 0;
       for (int grp_i = cgroup_id, it = 0; grp_i < n_groups; grp_i += n_cgroups, ++it) {
         uint64_t mask = PRE ? 0ull : ~0ull;                    // pre-projected latents: no lin_z chunk is executed

@@ -9,3 +9,8 @@ timeout 600 python bench.py --precision $prec --latent-table $tab --steps 3 --wa
 python -c "
 import json;d=json.loads(open('gpurun_out/ab5_${prec}_${which}_$tab.json').read().strip().splitlines()[-1]);print('$prec table=$tab $which: %.1f ms  %.0f rays/s'%(d['ms_per_step'],d['value']))"
 done; done; done
+unset SCENERF_B200_LIB
+for tab in 1 0; do
+SRF_TC_PROF=1 timeout 600 python bench.py --precision fp16 --latent-table $tab --steps 2 --warmup 3 --no-variants --no-cpu-baseline --no-extras > gpurun_out/ab5_prof_$tab.json 2> gpurun_out/ab5_prof_$tab.err
+grep prof gpurun_out/ab5_prof_$tab.err | grep -E "CTA=3065" | tail -1 | cut -c40-330
+done
