@@ -46,6 +46,10 @@ def workload(name):
         cfg = synth.config_C()
         pix = synth.grid_pixels(cfg.img_W, cfg.img_H)
         desc = "C: BundleFusion 640x480 full frame, 307200 rays x 96 samples"
+    elif name == "Bp":
+        cfg = synth.config_B(name="Bp", sphere_W=1500, sphere_H=452)
+        pix = synth.grid_pixels(cfg.img_W, cfg.img_H)
+        desc = "B': config B's frame (453620 rays x 128 samples) over the reference-default 1500x452 sphere grid (420 MB pyramid)"
     else:
         cfg = synth.config_B()
         pix = synth.grid_pixels(cfg.img_W, cfg.img_H)
@@ -1013,7 +1017,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="B", choices=["A", "B", "C", "D", "E", "sweep", "train", "decoder"])
+    ap.add_argument("--workload", default="B", choices=["A", "B", "Bp", "C", "D", "E", "sweep", "train", "decoder"])
     ap.add_argument("--train-matmul", default="fp32", choices=["fp32", "tf32"], help="--workload train: GEMM engine")
     ap.add_argument("--sweep-poses", type=int, default=63)
     ap.add_argument("--sweep-scale", type=int, default=2)
